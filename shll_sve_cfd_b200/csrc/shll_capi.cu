@@ -1,0 +1,573 @@
+// shll_capi.cu -- the C ABI of libshll_b200.so (include/shll_b200.h): context, device buffers, launches.
+//
+// Device memory of one context (one slab on one GPU):
+//   state : 2 (ping-pong) x ncomp planes, FP32.  2D plane = (nx + 2*HALO_ROWS) rows of ny floats, rows -2,-1 and
+//           nx,nx+1 being halo rows; 1D plane = PAD1D + roundup4(n) + PAD1D floats, cells -2,-1 / n,n+1 being halo
+//           cells.  One cudaMalloc, so that one CUDA-IPC handle exposes both buffers to the neighbour slabs.
+//   flags : halo-arrival flags / edge counters / error word (see halo_sync.cuh).
+// There is no host fallback anywhere in this file: every entry point either runs CUDA work or returns an error.
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "../../include/shll_b200.h"
+#include "shll_internal.h"
+
+using namespace shll;
+
+namespace {
+
+constexpr int HALO_ROWS = 2;
+constexpr int FLAG_WORDS = 64;  // [0]=arrived from lower, [1]=arrived from upper, [2]=cnt_lo, [3]=cnt_hi, [4]=err, [8]=cfl
+
+thread_local char g_create_error[512] = "";
+
+__global__ void fill_kernel(float *p, float v, size_t n)
+{
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+}  // namespace
+
+struct shll_ctx {
+    shll_config cfg;
+    int ncomp;
+    long ncells;          // owned cells
+    size_t plane_elems;   // floats per plane, including halos / padding
+    size_t interior_off;  // floats from the plane start to owned cell 0
+    float *state;         // 2 * ncomp * plane_elems floats
+    unsigned *flags;
+    float *scratch;       // lazily allocated: primitive download (ncomp + 1 planes of ncells)
+    int cur;              // which ping-pong buffer holds the current state
+    bool has_state;
+    cudaStream_t stream;
+    cudaEvent_t ev0, ev1;
+    long launches;
+    unsigned state_index;  // time steps taken since creation (monotonic; halo flags are expressed in it)
+    unsigned epoch;        // step launches since creation
+    KernelKey key;
+    int ntiles, nchunks;
+    char variant[128];
+    char err[512];
+    // neighbours
+    float *peer_state[2];     // [0] lower, [1] upper: base of the neighbour's state allocation (mapped)
+    unsigned *peer_flags[2];
+    bool peer_ipc[2];         // opened with cudaIpcOpenMemHandle (must be closed)
+    shll_peer_desc peer_desc[2];
+    bool connected[2];
+
+    float *plane(int buf, int k) const { return state + ((size_t)buf * ncomp + k) * plane_elems + interior_off; }
+};
+
+namespace {
+
+int fail(shll_ctx *c, int code, const char *fmt, ...)
+{
+    char *dst = c ? c->err : g_create_error;
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(dst, 512, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CK(ctx, call)                                                                                        \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, SHLL_E_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+bool is_pow2(float x)
+{
+    int e;
+    return x > 0.0f && std::frexp(x, &e) == 0.5f;
+}
+
+int env_int(const char *name, int dflt)
+{
+    const char *s = getenv(name);
+    return (s && *s) ? atoi(s) : dflt;
+}
+
+// Choose vector width, tiles and row chunks for the 2D kernel.
+void plan_2d(shll_ctx *c)
+{
+    const shll_config &g = c->cfg;
+    int vec = g.variant > 0 ? g.variant : env_int("SHLL_VEC", 0);
+    if (vec != 1 && vec != 2 && vec != 4) vec = (g.order == 1) ? 2 : 1;  // defaults from the B200 sweep in DESIGN.md
+    while (vec > 1 && (g.ny % vec != 0 || g.ny < 32 * vec)) vec >>= 1;
+    c->key.vec = vec;
+    const int hl = (g.order + vec - 1) / vec;
+    const int useful = (32 - 2 * hl) * vec;
+    c->ntiles = (g.ny + useful - 1) / useful;
+    int rpc = env_int("SHLL_ROWS_PER_CHUNK", 64);
+    if (rpc < 2) rpc = 2;
+    int nchunks = (g.nx + rpc - 1) / rpc;
+    if (nchunks < 1) nchunks = 1;
+    while (nchunks > 1 && g.nx / nchunks < 2) nchunks--;
+    c->nchunks = nchunks;
+}
+
+void plan_1d(shll_ctx *c)
+{
+    c->key.vec = 4;
+    c->ntiles = (c->cfg.nx + 119) / 120;
+    c->nchunks = 1;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shll_abi_version(void) { return SHLL_ABI_VERSION; }
+
+const char *shll_last_error(const shll_ctx *ctx) { return ctx ? ctx->err : g_create_error; }
+
+int shll_count_steps(float dt, float total_time, long *nsteps)
+{
+    if (!nsteps || !(dt > 0.0f)) return fail(nullptr, SHLL_E_INVAL, "shll_count_steps: bad arguments");
+    // base_shll.c:200,208,216-217 -- the reference's clock is a float accumulator.
+    volatile float t = 0.0f;
+    long n = 0;
+    while (t < total_time) {
+        float tn = t + dt;
+        if (tn == t) return fail(nullptr, SHLL_E_INVAL, "float clock stalls at t=%g with dt=%g (the reference would never terminate)", (double)t, (double)dt);
+        t = tn;
+        n++;
+    }
+    *nsteps = n;
+    return SHLL_OK;
+}
+
+int shll_create(shll_ctx **out, const shll_config *cfg)
+{
+    if (!out || !cfg) return fail(nullptr, SHLL_E_INVAL, "shll_create: null argument");
+    *out = nullptr;
+    if (cfg->struct_size != sizeof(shll_config))
+        return fail(nullptr, SHLL_E_INVAL, "shll_create: struct_size %u != %zu (ABI mismatch)", cfg->struct_size, sizeof(shll_config));
+    shll_config g = *cfg;
+    if (g.dims != 1 && g.dims != 2) return fail(nullptr, SHLL_E_INVAL, "dims must be 1 or 2");
+    if (g.dims == 1) g.ny = 1;
+    if (g.nx < 2 || (g.dims == 2 && g.ny < 2)) return fail(nullptr, SHLL_E_INVAL, "grid too small: nx=%d ny=%d", g.nx, g.ny);
+    if (g.order != 1 && g.order != 2) return fail(nullptr, SHLL_E_INVAL, "order must be 1 or 2");
+    if (g.bc != SHLL_BC_REFLECT && g.bc != SHLL_BC_OUTFLOW) return fail(nullptr, SHLL_E_INVAL, "bad bc");
+    if (g.limiter != SHLL_LIM_MINMOD && g.limiter != SHLL_LIM_MC) return fail(nullptr, SHLL_E_INVAL, "bad limiter");
+    if (g.mode != SHLL_MODE_STRICT && g.mode != SHLL_MODE_FAST) return fail(nullptr, SHLL_E_INVAL, "bad mode");
+    if (g.nranks < 1) g.nranks = 1;
+    if (g.rank < 0 || g.rank >= g.nranks) return fail(nullptr, SHLL_E_INVAL, "rank %d outside [0,%d)", g.rank, g.nranks);
+    if (g.nranks > 1 && g.nx < 2 * g.order) return fail(nullptr, SHLL_E_INVAL, "slab of %d rows is thinner than two halos", g.nx);
+    if (g.tform == SHLL_TFORM_AUTO) g.tform = (g.dims == 1 && g.order == 1) ? SHLL_TFORM_1D : SHLL_TFORM_2D;
+    if (g.dims == 2) g.tform = SHLL_TFORM_2D;
+    if (!(g.dt_on_dx > 0.0f) || (g.dims == 2 && !(g.dt_on_dy > 0.0f))) return fail(nullptr, SHLL_E_INVAL, "dt_on_dx / dt_on_dy must be positive");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, SHLL_E_CUDA, "no CUDA device available (%s); libshll_b200 has no CPU fallback",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    if (g.device < 0 || g.device >= ndev) return fail(nullptr, SHLL_E_INVAL, "device %d outside [0,%d)", g.device, ndev);
+
+    shll_ctx *c = new (std::nothrow) shll_ctx();
+    if (!c) return fail(nullptr, SHLL_E_NOMEM, "out of host memory");
+    memset(c, 0, sizeof(*c));
+    c->cfg = g;
+    c->ncomp = (g.dims == 1) ? 3 : 4;
+    c->ncells = (long)g.nx * g.ny;
+    if (g.dims == 1) {
+        c->interior_off = PAD1D;
+        c->plane_elems = round_up((size_t)PAD1D + round_up((size_t)g.nx, 4) + PAD1D + 4, 64);
+    } else {
+        c->interior_off = (size_t)HALO_ROWS * g.ny;
+        c->plane_elems = round_up((size_t)(g.nx + 2 * HALO_ROWS) * g.ny, 64);
+    }
+    c->key.order = g.order;
+    c->key.bc = g.bc;
+    c->key.lim = g.limiter;
+    c->key.mode = g.mode;
+    c->key.tform = g.tform;
+    c->key.pow2 = is_pow2(g.dt_on_dx) && (g.dims == 1 || is_pow2(g.dt_on_dy));
+    if (g.dims == 1) plan_1d(c); else plan_2d(c);
+    snprintf(c->variant, sizeof(c->variant), "step%dd_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, g.order,
+             g.bc == SHLL_BC_REFLECT ? "reflect" : "outflow", g.order == 2 ? (g.limiter == SHLL_LIM_MC ? "mc_" : "minmod_") : "",
+             g.mode == SHLL_MODE_STRICT ? "strict" : "fast", c->key.pow2 ? "pow2" : "gendt", c->key.vec, c->ntiles, c->nchunks);
+
+#define CKC(call)                                                                                 \
+    do {                                                                                          \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            int rc_ = fail(nullptr, e_ == cudaErrorMemoryAllocation ? SHLL_E_NOMEM : SHLL_E_CUDA, \
+                           "%s failed: %s", #call, cudaGetErrorString(e_));                       \
+            shll_destroy(c);                                                                      \
+            return rc_;                                                                           \
+        }                                                                                         \
+    } while (0)
+    CKC(cudaSetDevice(g.device));
+    CKC(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    CKC(cudaEventCreate(&c->ev0));
+    CKC(cudaEventCreate(&c->ev1));
+    const size_t state_bytes = (size_t)2 * c->ncomp * c->plane_elems * sizeof(float);
+    CKC(cudaMalloc(&c->state, state_bytes));
+    CKC(cudaMalloc(&c->flags, FLAG_WORDS * sizeof(unsigned)));
+    CKC(cudaMemsetAsync(c->flags, 0, FLAG_WORDS * sizeof(unsigned), c->stream));
+    // Fill everything (halos, padding) with a benign gas state (1.0f bit pattern) so unused lanes never see NaNs.
+    fill_kernel<<<1024, 256, 0, c->stream>>>(c->state, 1.0f, state_bytes / sizeof(float));
+    CKC(cudaGetLastError());
+    CKC(cudaStreamSynchronize(c->stream));
+#undef CKC
+    *out = c;
+    return SHLL_OK;
+}
+
+int shll_destroy(shll_ctx *c)
+{
+    if (!c) return SHLL_OK;
+    cudaSetDevice(c->cfg.device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    for (int s = 0; s < 2; s++) {
+        if (c->connected[s] && c->peer_ipc[s]) {
+            if (c->peer_state[s]) cudaIpcCloseMemHandle(c->peer_state[s]);
+            if (c->peer_flags[s]) cudaIpcCloseMemHandle(c->peer_flags[s]);
+        }
+    }
+    if (c->scratch) cudaFree(c->scratch);
+    if (c->state) cudaFree(c->state);
+    if (c->flags) cudaFree(c->flags);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return SHLL_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ halo push
+namespace {
+
+// Copies this slab's edge rows / cells of the *current* buffer into the neighbours' halo storage and raises their
+// flags.  Used once after shll_upload_u (the step kernels do it themselves afterwards).
+__global__ void push_halo_kernel(const float *src_lo, const float *src_hi, float *dst_lo, float *dst_hi, long count,
+                                 int ncomp, size_t src_plane, size_t dst_plane_lo, size_t dst_plane_hi,
+                                 unsigned *flag_lo, unsigned *flag_hi, unsigned value)
+{
+    for (int k = 0; k < ncomp; k++) {
+        for (long t = threadIdx.x; t < count; t += blockDim.x) {
+            if (dst_lo) dst_lo[k * dst_plane_lo + t] = src_lo[k * src_plane + t];
+            if (dst_hi) dst_hi[k * dst_plane_hi + t] = src_hi[k * src_plane + t];
+        }
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        if (flag_lo) st_release_sys(flag_lo, value);
+        if (flag_hi) st_release_sys(flag_hi, value);
+    }
+}
+
+// geometry of a neighbour's plane, from its descriptor
+size_t peer_plane_elems(const shll_peer_desc &d)
+{
+    if (d.dims == 1) return round_up((size_t)PAD1D + round_up((size_t)d.nx, 4) + PAD1D + 4, 64);
+    return round_up((size_t)(d.nx + 2 * HALO_ROWS) * d.ny, 64);
+}
+size_t peer_interior_off(const shll_peer_desc &d) { return d.dims == 1 ? (size_t)PAD1D : (size_t)HALO_ROWS * d.ny; }
+
+// Pointer to the place in neighbour `side`'s buffer `buf`, plane k, where OUR edge data must land.
+//   side 0 (lower neighbour): its upper halo = rows nx_peer .. ;  side 1 (upper neighbour): its lower halo = rows -order ..
+float *peer_halo_ptr(const shll_ctx *c, int side, int buf, int k)
+{
+    const shll_peer_desc &d = c->peer_desc[side];
+    const size_t pe = peer_plane_elems(d);
+    float *base = c->peer_state[side] + ((size_t)buf * c->ncomp + k) * pe + peer_interior_off(d);
+    const long row = c->cfg.dims == 1 ? 1 : c->cfg.ny;
+    if (side == 0) return base + (long)d.nx * row;
+    return base - (long)c->cfg.order * row;
+}
+
+bool multi(const shll_ctx *c) { return c->cfg.nranks > 1; }
+
+int check_connected(shll_ctx *c)
+{
+    if (!multi(c)) return SHLL_OK;
+    if (c->cfg.rank > 0 && !c->connected[0]) return fail(c, SHLL_E_STATE, "rank %d: lower neighbour not connected (shll_peer_connect)", c->cfg.rank);
+    if (c->cfg.rank < c->cfg.nranks - 1 && !c->connected[1]) return fail(c, SHLL_E_STATE, "rank %d: upper neighbour not connected", c->cfg.rank);
+    return SHLL_OK;
+}
+
+int launch_one_step(shll_ctx *c)
+{
+    const shll_config &g = c->cfg;
+    const int in = c->cur, outb = c->cur ^ 1;
+    const bool lo_wall = (g.rank == 0), hi_wall = (g.rank == g.nranks - 1);
+    HaloSync S;
+    memset(&S, 0, sizeof(S));
+    if (multi(c)) {
+        S.enabled = 1;
+        S.want = c->state_index + 1;
+        S.post = c->state_index + 2;
+        S.epoch = c->epoch + 1;
+        S.wait_lo = lo_wall ? nullptr : c->flags + 0;
+        S.wait_hi = hi_wall ? nullptr : c->flags + 1;
+        S.sig_lo = lo_wall ? nullptr : c->peer_flags[0] + 1;  // we are the lower neighbour's UPPER neighbour
+        S.sig_hi = hi_wall ? nullptr : c->peer_flags[1] + 0;
+        S.cnt_lo = c->flags + 2;
+        S.cnt_hi = c->flags + 3;
+        S.err = c->flags + 4;
+        S.timeout_ns = (unsigned long long)env_int("SHLL_HALO_TIMEOUT_MS", 5000) * 1000000ull;
+    }
+    cudaError_t e;
+    if (g.dims == 2) {
+        Step2DParams P;
+        memset(&P, 0, sizeof(P));
+        for (int k = 0; k < 4; k++) {
+            P.in[k] = c->plane(in, k);
+            P.out[k] = c->plane(outb, k);
+            P.lo_peer[k] = (multi(c) && !lo_wall) ? peer_halo_ptr(c, 0, outb, k) : nullptr;
+            P.hi_peer[k] = (multi(c) && !hi_wall) ? peer_halo_ptr(c, 1, outb, k) : nullptr;
+        }
+        P.nx = g.nx; P.ny = g.ny;
+        P.lo_wall = lo_wall; P.hi_wall = hi_wall;
+        P.ntiles = c->ntiles; P.nchunks = c->nchunks;
+        P.dtdx = g.dt_on_dx; P.dtdy = g.dt_on_dy;
+        P.half_dtdx = 0.5f * g.dt_on_dx; P.half_dtdy = 0.5f * g.dt_on_dy;
+        P.alpha = g.alpha;
+        S.edge_warps_lo = S.edge_warps_hi = (unsigned)c->ntiles;
+        P.sync = S;
+        const int warps = c->ntiles * c->nchunks;
+        dim3 block(128), grid((warps + 3) / 4);
+        if (g.order == 1) e = launch_step2d_o1(c->key, P, grid, block, c->stream);
+        else if (g.mode == SHLL_MODE_STRICT) e = launch_step2d_o2_strict(c->key, P, grid, block, c->stream);
+        else e = launch_step2d_o2_fast(c->key, P, grid, block, c->stream);
+    } else {
+        Step1DParams P;
+        memset(&P, 0, sizeof(P));
+        for (int k = 0; k < 3; k++) {
+            P.in[k] = c->plane(in, k);
+            P.out[k] = c->plane(outb, k);
+            P.lo_peer[k] = (multi(c) && !lo_wall) ? peer_halo_ptr(c, 0, outb, k) : nullptr;
+            P.hi_peer[k] = (multi(c) && !hi_wall) ? peer_halo_ptr(c, 1, outb, k) : nullptr;
+        }
+        P.n = g.nx;
+        P.lo_wall = lo_wall; P.hi_wall = hi_wall;
+        P.ntiles = c->ntiles;
+        P.dtdx = g.dt_on_dx; P.half_dtdx = 0.5f * g.dt_on_dx; P.alpha = g.alpha;
+        S.edge_warps_lo = 1;
+        S.edge_warps_hi = (unsigned)((g.nx - 1) / 120 - (g.nx - g.order) / 120 + 1);
+        P.sync = S;
+        dim3 block(256), grid((c->ntiles + 7) / 8);
+        e = launch_step1d(c->key, P, grid, block, c->stream);
+    }
+    if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "step kernel launch failed (%s): %s", c->variant, cudaGetErrorString(e));
+    c->cur = outb;
+    c->state_index++;
+    c->epoch++;
+    c->launches++;
+    return SHLL_OK;
+}
+
+int check_halo_error(shll_ctx *c)
+{
+    if (!multi(c)) return SHLL_OK;
+    unsigned err = 0;
+    CK(c, cudaMemcpyAsync(&err, c->flags + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    if (err) return fail(c, SHLL_E_TIMEOUT, "rank %d: a neighbour's halo did not arrive within the timeout", c->cfg.rank);
+    return SHLL_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int shll_upload_u(shll_ctx *c, const float *const u[4])
+{
+    if (!c || !u) return fail(c, SHLL_E_INVAL, "shll_upload_u: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    int rc = check_connected(c);
+    if (rc) return rc;
+    for (int k = 0; k < c->ncomp; k++) {
+        if (!u[k]) return fail(c, SHLL_E_INVAL, "shll_upload_u: u[%d] is null", k);
+        CK(c, cudaMemcpyAsync(c->plane(c->cur, k), u[k], (size_t)c->ncells * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    }
+    c->has_state = true;
+    if (multi(c)) {
+        // publish our edge rows of the freshly uploaded state to the neighbours' halos
+        const shll_config &g = c->cfg;
+        const bool lo_wall = (g.rank == 0), hi_wall = (g.rank == g.nranks - 1);
+        const long row = g.dims == 1 ? 1 : g.ny;
+        const long count = (long)g.order * row;
+        const float *src_lo = c->plane(c->cur, 0);
+        const float *src_hi = c->plane(c->cur, 0) + ((long)g.nx - g.order) * row;
+        float *dst_lo = lo_wall ? nullptr : peer_halo_ptr(c, 0, c->cur, 0);
+        float *dst_hi = hi_wall ? nullptr : peer_halo_ptr(c, 1, c->cur, 0);
+        push_halo_kernel<<<1, 1024, 0, c->stream>>>(src_lo, src_hi, dst_lo, dst_hi, count, c->ncomp, c->plane_elems,
+                                                     lo_wall ? 0 : peer_plane_elems(c->peer_desc[0]),
+                                                     hi_wall ? 0 : peer_plane_elems(c->peer_desc[1]),
+                                                     lo_wall ? nullptr : c->peer_flags[0] + 1,
+                                                     hi_wall ? nullptr : c->peer_flags[1] + 0, c->state_index + 1);
+        CK(c, cudaGetLastError());
+        c->launches++;
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SHLL_OK;
+}
+
+int shll_download_u(shll_ctx *c, float *const u[4])
+{
+    if (!c || !u) return fail(c, SHLL_E_INVAL, "shll_download_u: null argument");
+    if (!c->has_state) return fail(c, SHLL_E_STATE, "shll_download_u before shll_upload_u");
+    CK(c, cudaSetDevice(c->cfg.device));
+    for (int k = 0; k < c->ncomp; k++) {
+        if (!u[k]) return fail(c, SHLL_E_INVAL, "shll_download_u: u[%d] is null", k);
+        CK(c, cudaMemcpyAsync(u[k], c->plane(c->cur, k), (size_t)c->ncells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CK(c, cudaStreamSynchronize(c->stream));
+    return check_halo_error(c);
+}
+
+int shll_download_p(shll_ctx *c, float *const p[4], float *a)
+{
+    if (!c || !p) return fail(c, SHLL_E_INVAL, "shll_download_p: null argument");
+    if (!c->has_state) return fail(c, SHLL_E_STATE, "shll_download_p before shll_upload_u");
+    CK(c, cudaSetDevice(c->cfg.device));
+    if (!c->scratch) CK(c, cudaMalloc(&c->scratch, (size_t)(c->ncomp + 1) * c->ncells * sizeof(float)));
+    const float *uin[4] = {nullptr, nullptr, nullptr, nullptr};
+    float *pout[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < c->ncomp; k++) {
+        uin[k] = c->plane(c->cur, k);
+        pout[k] = c->scratch + (size_t)k * c->ncells;
+    }
+    float *adev = c->scratch + (size_t)c->ncomp * c->ncells;
+    CK(c, launch_prim(c->cfg.dims, c->cfg.mode, c->cfg.tform, uin, pout, adev, c->ncells, c->stream));
+    c->launches++;
+    for (int k = 0; k < c->ncomp; k++) {
+        if (!p[k]) return fail(c, SHLL_E_INVAL, "shll_download_p: p[%d] is null", k);
+        CK(c, cudaMemcpyAsync(p[k], pout[k], (size_t)c->ncells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (a) CK(c, cudaMemcpyAsync(a, adev, (size_t)c->ncells * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return check_halo_error(c);
+}
+
+int shll_run(shll_ctx *c, long nsteps)
+{
+    if (!c || nsteps < 0) return fail(c, SHLL_E_INVAL, "shll_run: bad argument");
+    if (!c->has_state) return fail(c, SHLL_E_STATE, "shll_run before shll_upload_u");
+    CK(c, cudaSetDevice(c->cfg.device));
+    int rc = check_connected(c);
+    if (rc) return rc;
+    for (long s = 0; s < nsteps; s++) {
+        rc = launch_one_step(c);
+        if (rc) return rc;
+    }
+    return SHLL_OK;
+}
+
+int shll_sync(shll_ctx *c)
+{
+    if (!c) return fail(c, SHLL_E_INVAL, "shll_sync: null context");
+    CK(c, cudaSetDevice(c->cfg.device));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return check_halo_error(c);
+}
+
+int shll_run_timed(shll_ctx *c, long nsteps, float *ms)
+{
+    if (!c || !ms) return fail(c, SHLL_E_INVAL, "shll_run_timed: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    CK(c, cudaEventRecord(c->ev0, c->stream));
+    int rc = shll_run(c, nsteps);
+    if (rc) return rc;
+    CK(c, cudaEventRecord(c->ev1, c->stream));
+    CK(c, cudaEventSynchronize(c->ev1));
+    CK(c, cudaEventElapsedTime(ms, c->ev0, c->ev1));
+    return check_halo_error(c);
+}
+
+int shll_max_cfl(shll_ctx *c, float *cfl)
+{
+    if (!c || !cfl) return fail(c, SHLL_E_INVAL, "shll_max_cfl: null argument");
+    if (!c->has_state) return fail(c, SHLL_E_STATE, "shll_max_cfl before shll_upload_u");
+    CK(c, cudaSetDevice(c->cfg.device));
+    const float *uin[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < c->ncomp; k++) uin[k] = c->plane(c->cur, k);
+    float *out_dev = reinterpret_cast<float *>(c->flags + 8);
+    CK(c, cudaMemsetAsync(out_dev, 0, sizeof(float), c->stream));
+    // 2D planes are contiguous over the owned rows; 1D over the owned cells.
+    CK(c, launch_max_cfl(c->cfg.dims, c->cfg.mode, c->cfg.tform, uin, c->ncells, c->cfg.dt_on_dx, c->cfg.dt_on_dy, out_dev, c->stream));
+    c->launches++;
+    CK(c, cudaMemcpyAsync(cfl, out_dev, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    return SHLL_OK;
+}
+
+long shll_launch_count(const shll_ctx *c) { return c ? c->launches : 0; }
+const char *shll_variant_name(const shll_ctx *c) { return c ? c->variant : ""; }
+
+int shll_peer_export(shll_ctx *c, shll_peer_desc *d)
+{
+    if (!c || !d) return fail(c, SHLL_E_INVAL, "shll_peer_export: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    memset(d, 0, sizeof(*d));
+    static_assert(sizeof(cudaIpcMemHandle_t) == SHLL_IPC_BYTES, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    CK(c, cudaIpcGetMemHandle(&h, c->state));
+    memcpy(d->state_handle, &h, SHLL_IPC_BYTES);
+    CK(c, cudaIpcGetMemHandle(&h, c->flags));
+    memcpy(d->flag_handle, &h, SHLL_IPC_BYTES);
+    d->pid = (int64_t)getpid();
+    d->state_ptr = (uint64_t)(uintptr_t)c->state;
+    d->flag_ptr = (uint64_t)(uintptr_t)c->flags;
+    d->device = c->cfg.device;
+    d->nx = c->cfg.nx; d->ny = c->cfg.ny; d->dims = c->cfg.dims; d->order = c->cfg.order;
+    return SHLL_OK;
+}
+
+int shll_peer_connect(shll_ctx *c, int side, const shll_peer_desc *d)
+{
+    if (!c || !d || (side != -1 && side != 1)) return fail(c, SHLL_E_INVAL, "shll_peer_connect: bad argument");
+    const int s = side < 0 ? 0 : 1;
+    if (c->connected[s]) return fail(c, SHLL_E_STATE, "side %d already connected", side);
+    if (d->dims != c->cfg.dims || d->ny != c->cfg.ny || d->order != c->cfg.order)
+        return fail(c, SHLL_E_INVAL, "neighbour geometry mismatch (dims %d/%d ny %d/%d order %d/%d)", d->dims, c->cfg.dims, d->ny, c->cfg.ny, d->order, c->cfg.order);
+    CK(c, cudaSetDevice(c->cfg.device));
+    if (d->pid == (int64_t)getpid()) {
+        // same process: plain peer pointers
+        if (d->device != c->cfg.device) {
+            int can = 0;
+            CK(c, cudaDeviceCanAccessPeer(&can, c->cfg.device, d->device));
+            if (!can) return fail(c, SHLL_E_CUDA, "device %d cannot access peer %d", c->cfg.device, d->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(d->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) CK(c, e);
+            (void)cudaGetLastError();
+        }
+        c->peer_state[s] = reinterpret_cast<float *>((uintptr_t)d->state_ptr);
+        c->peer_flags[s] = reinterpret_cast<unsigned *>((uintptr_t)d->flag_ptr);
+        c->peer_ipc[s] = false;
+    } else {
+        cudaIpcMemHandle_t h;
+        void *p = nullptr;
+        memcpy(&h, d->state_handle, SHLL_IPC_BYTES);
+        CK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_state[s] = static_cast<float *>(p);
+        memcpy(&h, d->flag_handle, SHLL_IPC_BYTES);
+        CK(c, cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+        c->peer_flags[s] = static_cast<unsigned *>(p);
+        c->peer_ipc[s] = true;
+    }
+    c->peer_desc[s] = *d;
+    c->connected[s] = true;
+    return SHLL_OK;
+}
+
+}  // extern "C"

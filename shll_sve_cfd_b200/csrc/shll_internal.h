@@ -1,0 +1,27 @@
+// shll_internal.h -- launcher interface between the C-ABI layer (shll_capi.cu) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "step1d.cuh"
+#include "step2d.cuh"
+
+namespace shll {
+
+struct KernelKey {
+    int order, bc, lim, mode, vec, tform;
+    bool pow2;
+};
+
+// Each returns cudaSuccess / the launch error; cudaErrorInvalidValue for a combination that was not instantiated.
+cudaError_t launch_step2d_o1(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);
+cudaError_t launch_step2d_o2_strict(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);
+cudaError_t launch_step2d_o2_fast(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);
+cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s);
+
+// Compute_P_from_U on the device (for shll_download_p) and the diagnostic CFL reduction.
+cudaError_t launch_prim(int dims, int mode, int tform, const float *const u[4], float *const p[4], float *a, long ncells,
+                        cudaStream_t s);
+cudaError_t launch_max_cfl(int dims, int mode, int tform, const float *const u[4], long ncells, float dtdx, float dtdy,
+                           float *out_dev, cudaStream_t s);
+
+}  // namespace shll

@@ -1,0 +1,150 @@
+// step1d.cuh -- one fused SHLL time step on a 1D slab (base_shll.c and the derived 1D 2nd-order program).
+//
+// Layout: three FP32 planes (rho, rho*u, E), each padded by PAD1D floats on both sides so that the first owned
+// cell is 16-byte aligned and the halo cells of a slab (2 per side) live at indices -2,-1 and n,n+1.
+//
+// A warp owns 120 consecutive cells: every lane loads one float4 (4 cells) per plane -> 512 contiguous bytes per
+// plane per warp; lanes 0 and 31 are halo lanes that recompute the neighbouring tiles' edge cells, so the +-1 / +-2
+// cell stencil is closed with in-thread neighbours plus one shuffle per plane per direction, and no warp ever
+// talks to another.  Algorithmic traffic: 3 planes read + 3 written = 24 B per cell per step.
+#pragma once
+#include "halo_sync.cuh"
+#include "shll_math.cuh"
+
+namespace shll {
+
+constexpr int PAD1D = 4;
+
+struct Step1DParams {
+    const float *in[3];  // plane base = local cell 0
+    float *out[3];
+    float *lo_peer[3];   // lower neighbour's cells n_peer.. (its upper halo), or NULL
+    float *hi_peer[3];   // upper neighbour's cells -ORDER.. (its lower halo), or NULL
+    int n;
+    int lo_wall, hi_wall;
+    int ntiles;
+    float dtdx, half_dtdx, alpha;
+    HaloSync sync;  // multi-GPU only
+};
+
+template <int ORDER, int BC, int LIM, int MODE, int TFORM, bool POW2>
+__global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
+{
+    constexpr int VEC = 4;
+    constexpr int USEFUL = 30 * VEC;
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= P.ntiles) return;
+    const int n = P.n;
+    const int j0 = tile * USEFUL + (lane - 1) * VEC;  // >= -4: inside the padding
+    // last float4 that is still inside the allocation [-PAD1D, roundup4(n) + PAD1D)
+    const int jmax = ((n + 3) & ~3);
+    const int jl = min(j0, jmax);
+    const bool lo_wall = P.lo_wall != 0, hi_wall = P.hi_wall != 0;
+    // warps owning one of the first / last ORDER cells exchange halos with the neighbour GPUs
+    const int own_lo = tile * USEFUL, own_hi = min(own_lo + USEFUL, n);  // owned cells [own_lo, own_hi)
+    const bool touch_lo = (own_lo < ORDER), touch_hi = (own_hi > n - ORDER) && (own_lo < n);
+    if (P.sync.enabled) {
+        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
+        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
+    }
+
+    float u[VEC][3], fp[VEC][3], fm[VEC][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float4 t = *reinterpret_cast<const float4 *>(P.in[k] + jl);  // plain (coherent) load: halo cells are written by a peer GPU
+        u[0][k] = t.x; u[1][k] = t.y; u[2][k] = t.z; u[3][k] = t.w;
+    }
+#pragma unroll
+    for (int v = 0; v < VEC; v++) cell_flux_1d<MODE, TFORM>(u[v], fp[v], fm[v]);
+
+    bool at_lo[VEC], at_hi[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        at_lo[v] = lo_wall && (j0 + v == 0);
+        at_hi[v] = hi_wall && (j0 + v == n - 1);
+    }
+
+    float uo[VEC][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float fp_from_lo = __shfl_up_sync(full, fp[VEC - 1][k], 1);  // F+ of cell j-1
+        float fm_from_hi = __shfl_down_sync(full, fm[0][k], 1);      // F- of cell j+1
+        float fpL[VEC], fmR[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            fpL[v] = (v > 0) ? fp[v > 0 ? v - 1 : 0][k] : fp_from_lo;
+            fmR[v] = (v < VEC - 1) ? fm[v < VEC - 1 ? v + 1 : 0][k] : fm_from_hi;
+        }
+        float t1[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {
+            // reflective ends: (-,+,-) on (rho, rho*u, E), base_shll.c:95-97,108-110; outflow: own flux
+            float left, right;
+            if (BC == BC_REFLECT) {
+                left = at_lo[v] ? ((k == 1) ? fm[v][k] : -fm[v][k]) : fpL[v];
+                right = at_hi[v] ? ((k == 1) ? fp[v][k] : -fp[v][k]) : fmR[v];
+            } else {
+                left = at_lo[v] ? fp[v][k] : fpL[v];
+                right = at_hi[v] ? fm[v][k] : fmR[v];
+            }
+            t1[v] = apply_first<MODE>(u[v][k], P.dtdx, flux_sum<MODE>(fp[v][k], fm[v][k], right, left));  // base_shll.c:124
+        }
+        if (ORDER == 2) {
+            float fm_from_lo = __shfl_up_sync(full, fm[VEC - 1][k], 1);
+            float fp_from_hi = __shfl_down_sync(full, fp[0][k], 1);
+            float dfp[VEC], dfm[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                float fmL = (v > 0) ? fm[v > 0 ? v - 1 : 0][k] : fm_from_lo;
+                float fpR = (v < VEC - 1) ? fp[v < VEC - 1 ? v + 1 : 0][k] : fp_from_hi;
+                bool edge = at_lo[v] || at_hi[v];
+                dfp[v] = edge ? 0.0f : limited_slope<LIM>(fpL[v], fp[v][k], fpR, P.alpha);
+                dfm[v] = edge ? 0.0f : limited_slope<LIM>(fmL, fm[v][k], fmR[v], P.alpha);
+            }
+            float dfp_from_lo = __shfl_up_sync(full, dfp[VEC - 1], 1);
+            float dfm_from_hi = __shfl_down_sync(full, dfm[0], 1);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                float ldf = (v > 0) ? dfp[v > 0 ? v - 1 : 0] : dfp_from_lo;
+                float rdf = (v < VEC - 1) ? dfm[v < VEC - 1 ? v + 1 : 0] : dfm_from_hi;
+                ldf = at_lo[v] ? 0.0f : ldf;
+                rdf = at_hi[v] ? 0.0f : rdf;
+                t1[v] = apply_second<MODE, POW2>(t1[v], P.half_dtdx, slope_sum(dfp[v], dfm[v], rdf, ldf));
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; v++) uo[v][k] = t1[v];
+    }
+
+    const bool owner = !(lane == 0 || lane == 31 || j0 >= n);
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        if (!owner) continue;
+        if (j0 + VEC <= n) {
+            *reinterpret_cast<float4 *>(P.out[k] + j0) = make_float4(uo[0][k], uo[1][k], uo[2][k], uo[3][k]);
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; v++)
+                if (j0 + v < n) P.out[k][j0 + v] = uo[v][k];
+        }
+        // halo exchange fused into the step: edge cells go straight into the neighbour GPU's halo cells
+        if (P.lo_peer[k] != nullptr && j0 < ORDER) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++)
+                if (j0 + v < ORDER && j0 + v < n) P.lo_peer[k][j0 + v] = uo[v][k];
+        }
+        if (P.hi_peer[k] != nullptr && j0 + VEC > n - ORDER) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++)
+                if (j0 + v >= n - ORDER && j0 + v < n) P.hi_peer[k][j0 + v - (n - ORDER)] = uo[v][k];
+        }
+    }
+    if (P.sync.enabled) {
+        if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);
+        if (touch_hi) halo_arrive(P.sync, P.sync.cnt_hi, P.sync.edge_warps_hi, P.sync.sig_hi);
+    }
+}
+
+}  // namespace shll

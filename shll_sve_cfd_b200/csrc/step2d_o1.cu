@@ -1,0 +1,33 @@
+// step2d_o1.cu -- instantiations of the fused 2D step kernel, first order (base_shll_2d.c).
+#include "shll_internal.h"
+
+namespace shll {
+
+template <int BC, int MODE, int VEC>
+static cudaError_t go(const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s)
+{
+    step2d_kernel<1, BC, LIM_MINMOD, MODE, VEC, true><<<grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+
+template <int BC, int MODE>
+static cudaError_t by_vec(int vec, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s)
+{
+    switch (vec) {
+    case 1: return go<BC, MODE, 1>(p, grid, block, s);
+    case 2: return go<BC, MODE, 2>(p, grid, block, s);
+    case 4: return go<BC, MODE, 4>(p, grid, block, s);
+    }
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_step2d_o1(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s)
+{
+    if (k.bc == BC_REFLECT && k.mode == MODE_STRICT) return by_vec<BC_REFLECT, MODE_STRICT>(k.vec, p, grid, block, s);
+    if (k.bc == BC_REFLECT && k.mode == MODE_FAST) return by_vec<BC_REFLECT, MODE_FAST>(k.vec, p, grid, block, s);
+    if (k.bc == BC_OUTFLOW && k.mode == MODE_STRICT) return by_vec<BC_OUTFLOW, MODE_STRICT>(k.vec, p, grid, block, s);
+    if (k.bc == BC_OUTFLOW && k.mode == MODE_FAST) return by_vec<BC_OUTFLOW, MODE_FAST>(k.vec, p, grid, block, s);
+    return cudaErrorInvalidValue;
+}
+
+}  // namespace shll

@@ -1,0 +1,73 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def has_gpu() -> bool:
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+@pytest.fixture(scope="session")
+def manifest():
+    with open(os.path.join(GOLDEN_DIR, "MANIFEST.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    from oracle import oracle as O
+    O.build_lib()
+    return O
+
+
+def load_golden(case: str):
+    z = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
+    return z["u"], z["p"], int(z["steps"])
+
+
+def bits(a: np.ndarray) -> np.ndarray:
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def problem_from_manifest(entry: dict):
+    """MANIFEST entry -> shll_sve_cfd_b200.programs.Problem"""
+    from shll_sve_cfd_b200 import capi, programs
+    bc = capi.BC_REFLECT if entry["bc"] == "reflect" else capi.BC_OUTFLOW
+    lim = capi.LIM_MC if entry.get("limiter") == "mc" else capi.LIM_MINMOD
+    dims = entry["dims"]
+    tform = capi.TFORM_AUTO
+    if dims == 1 and entry["order"] == 2:
+        tform = capi.TFORM_2D
+    return programs.Problem(
+        name=entry["ref_binary"], dims=dims, nx=entry["nx"], ny=(entry["ny"] if dims == 2 else 1), order=entry["order"],
+        bc=bc, limiter=lim, alpha=entry.get("alpha", 1.25), ic=entry["ic"], total_time=entry["total"], tform=tform)
+
+
+def oracle_cfg_for(O, pb, nthreads=1):
+    from shll_sve_cfd_b200 import capi, programs
+    _, _, _, dtdx, dtdy = programs.time_constants(pb)
+    tform = pb.tform
+    if tform == capi.TFORM_AUTO:
+        tform = capi.TFORM_1D if (pb.dims == 1 and pb.order == 1) else capi.TFORM_2D
+    return O.make_cfg(pb.dims, pb.nx, pb.ny, order=pb.order, bc=pb.bc, limiter=pb.limiter, tform=tform, alpha=pb.alpha,
+                      dt_on_dx=float(dtdx), dt_on_dy=float(dtdy), nthreads=nthreads)
+
+
+ORACLE_IC = {"sod_1d": 0, "implosion": 1, "four_shock": 2, "config6": 3, "sod_x": 4}
