@@ -1,0 +1,304 @@
+#!/usr/bin/env python3
+"""bench.py -- the SHLL time-march hot path on N B200s (one process per GPU), and the reference's CPU path beside it.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--mode strict|fast]
+    python bench.py --impl reference ...          # the reference's own C program on the host cores
+
+A "step" is one time step of the fused kernel over the whole grid (one launch per GPU).  Workloads (BASELINE.json):
+
+    2d_o1      configs[2]: base_shll_2d.c scheme, 4096 x 4096 cells PER GPU (implosion IC, reflective walls).
+               N=1 is exactly configs[2]; for N>1 the domain is (4096*N) x 4096, slab-decomposed along x, one halo
+               row per side per step -> weak scaling.  This is the default and the headline line.
+    2d_o2      configs[4]: 2nd_order_base_shll.c scheme, 2048 x 16384 cells per GPU (16384^2 at 8 GPUs), two halo rows.
+    1d_o2      configs[3]: derived 1D 2nd-order, 2^26 cells TOTAL split over N GPUs (strong scaling), fixed step count.
+    1d_o1      base_shll.c scheme, 2^26 cells total (strong), for completeness.
+    1d_o2_64k  configs[1]: derived 1D 2nd-order, 65 536 cells on one GPU -- the launch-bound regime.
+
+The state (256 MiB per ping-pong buffer for 2d_o1) is larger than the 126 MB L2, so consecutive steps stream from HBM
+("l2": "inputs larger than L2" in config); workloads that fit in L2 say so.
+
+JSON keys follow the driver contract; `value` is cell-updates/s with the state resident in HBM (CUDA events on the
+library's stream, max over ranks); `e2e` is the same metric through the C ABI with host buffers: shll_upload_u from
+pinned host memory + K steps + shll_download_u inside the timed region (bytes are amortised per step).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (program, per-GPU nx, ny, scaling, bytes per cell-update, reference binary, description)
+    "2d_o1": dict(prog="base_shll_2d", nx=4096, ny=4096, scaling="weak", bpc=32, ref="ref_2d_o1_4096",
+                  desc="configs[2]: base_shll_2d.c 4096x4096 per GPU, 1st order, reflective, implosion IC"),
+    "2d_o2": dict(prog="2nd_order_base_shll", nx=2048, ny=16384, scaling="weak", bpc=32, ref="ref_2d_o2_4096",
+                  desc="configs[4]: 2nd_order_base_shll.c 2048x16384 per GPU (16384^2 at 8 GPUs), 2-row halos"),
+    "1d_o2": dict(prog="2nd_order_base_shll_1d", nx=1 << 26, ny=1, scaling="strong", bpc=24, ref="ref_1d_o2_slice_65536",
+                  desc="configs[3]: derived 1D 2nd-order Sod, 2^26 cells total, fixed step count"),
+    "1d_o1": dict(prog="base_shll", nx=1 << 26, ny=1, scaling="strong", bpc=24, ref="ref_1d_o1_65536",
+                  desc="base_shll.c scheme, 2^26 cells total, fixed step count"),
+    "1d_o2_64k": dict(prog="2nd_order_base_shll_1d", nx=65536, ny=1, scaling="strong", bpc=24, ref="ref_1d_o2_slice_65536",
+                      desc="configs[1]: derived 1D 2nd-order Sod, 65536 cells (launch-bound regime)"),
+}
+METRIC = "cell-updates/sec"
+UNIT = "cell-updates/s"
+L2_BYTES = 126e6
+
+
+def measured_peak_gbs():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md: 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def ref_time_per_step(exe, ncomp, ncells, k1, k2, threads=None):
+    """(t(k2) - t(k1)) / (k2 - k1) of the compiled reference program: cancels allocation and first touch."""
+    from oracle import oracle as O
+    r1 = O.run_ref(exe, ncomp, ncells, step_cap=k1, threads=threads, raw=False)
+    r2 = O.run_ref(exe, ncomp, ncells, step_cap=k2, threads=threads, raw=False)
+    return (r2["seconds"] - r1["seconds"]) / (k2 - k1), r1["seconds"], r2["seconds"]
+
+
+def cpu_reference_rate(workload, budget_s=20.0):
+    """The reference's own C program (oracle/_ref, kind 'reference') on one host core, bounded sample."""
+    from oracle import oracle as O
+    w = WORKLOADS[workload]
+    exe = w["ref"]
+    if not O.ref_available(exe):
+        return None
+    # cells the reference binary was built for (compile-time constants)
+    if exe.startswith("ref_1d_o2_slice_"):
+        n = int(exe.rsplit("_", 1)[1]); ncomp, ncells, cells_eff = 4, n * 4, n * 4   # NY=4 y-uniform run: 4 columns of real work
+    elif exe.startswith("ref_1d"):
+        n = int(exe.rsplit("_", 1)[1]); ncomp, ncells, cells_eff = 3, n, n
+    else:
+        n = int(exe.rsplit("_", 1)[1]); ncomp, ncells, cells_eff = 4, n * n, n * n
+    # calibrate with a tiny cap, then choose caps that fit the budget
+    k1, k2 = 1, 3
+    per_step, t1, t2 = ref_time_per_step(exe, ncomp, ncells, k1, k2)
+    per_step = max(per_step, 1e-7)
+    if per_step * 8 < budget_s:  # the probe was short: take a longer, better-averaged sample inside the budget
+        k2 = int(max(4, min(200000, budget_s * 0.6 / per_step)))
+        k1 = max(1, k2 // 4)
+        per_step, t1, t2 = ref_time_per_step(exe, ncomp, ncells, k1, k2)
+    return dict(value=cells_eff / per_step, unit=UNIT, cores=1, kind="reference",
+                sample=f"oracle/_ref/{exe} (reference source, gcc -O3) step caps {k1} and {k2}: {t1:.3f}s / {t2:.3f}s, "
+                       f"{cells_eff} cells per step", seconds_per_step=per_step)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    w = WORKLOADS[args.workload]
+    t0 = time.time()
+    base = cpu_reference_rate(args.workload, budget_s=30.0)
+    if base is None:
+        print(json.dumps({"impl": "reference", "unavailable": f"oracle/_ref/{w['ref']} was not built (needs /root/reference at build time)"}))
+        return 0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": base["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": base["seconds_per_step"] * 1e3, "higher_is_better": True,
+        "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"], "note": "reference C program, single thread "
+                   "(the reference has no threaded build of this scheme; base-omp is a different scheme/IC)"},
+        "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "e2e": {"value": base["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "wall_s": time.time() - t0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="2d_o1", choices=sorted(WORKLOADS))
+    ap.add_argument("--mode", default=os.environ.get("SHLL_BENCH_MODE", "strict"), choices=["strict", "fast"])
+    ap.add_argument("--nx", type=int, default=0, help="override per-GPU (weak) / total (strong) nx")
+    ap.add_argument("--ny", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import torch
+    import torch.distributed as dist
+    from shll_sve_cfd_b200 import capi, programs, slabs
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        print("bench.py: no CUDA device; the product path has no CPU fallback", file=sys.stderr)
+        return 2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    w = WORKLOADS[args.workload]
+    base = programs.PROGRAMS[w["prog"]]
+    nx_per = args.nx or w["nx"]
+    ny = (args.ny or w["ny"]) if base.dims == 2 else 1
+    nx_global = nx_per * world if w["scaling"] == "weak" else nx_per
+    pb = base.resized(nx_global, ny) if base.dims == 2 else base.resized(nx_global)
+    mode = capi.MODE_STRICT if args.mode == "strict" else capi.MODE_FAST
+    K, W = args.steps, args.warmup
+
+    ss = slabs.SlabSolver(pb, mode, dist if world > 1 else None, rank, world, local_rank,
+                          gather_device=torch.device("cuda", local_rank) if world > 1 else None)
+    s = ss.solver
+    nloc = ss.slab.nx_local * ny
+    ncomp = pb.ncomp
+    # pinned host buffers (torch is plumbing: pinned allocation, barriers)
+    host_in = torch.empty((ncomp, nloc), dtype=torch.float32, pin_memory=True)
+    host_out = torch.empty((ncomp, nloc), dtype=torch.float32, pin_memory=True)
+    host_in.numpy()[...] = ss.initial_state()
+    u_in, u_out = host_in.numpy(), host_out.numpy()
+
+    # ---- device-resident timing: W warm-up steps, then exactly K timed steps (CUDA events on the library's stream)
+    ss.upload(u_in)
+    s.run(W)
+    s.sync()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = s.launches
+    barrier()
+    ms = s.run_timed(K)
+    barrier()
+    launches = s.launches - launches0
+    ms = max_over_ranks(ms)
+    clocks = sampler.stop() if rank == 0 else None
+    total_cells = nx_global * ny
+    value = total_cells * K / (ms * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers (upload + K steps + download inside the timed region)
+    e2e = None
+    if not args.no_e2e:
+        barrier()
+        t0 = time.perf_counter()
+        ss.upload(u_in)
+        s.run(K)
+        s.download_u(u_out)
+        barrier()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        nbytes = ncomp * nloc * 4
+        e2e = {"value": total_cells * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes / K, "d2h_bytes_per_step": nbytes / K,
+               "seconds": t_e2e, "note": "one shll_upload_u (pinned host) + K steps + one shll_download_u per run; bytes amortised per step"}
+        checksum = float(u_out[0].astype(np.float64).sum())
+    variant = s.variant
+    ss.close()
+
+    if rank == 0:
+        peak, peak_src = measured_peak_gbs()
+        bytes_per_launch = w["bpc"] * nloc
+        achieved = bytes_per_launch / (ms * 1e-3 / K) / 1e9
+        traffic = None
+        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tr_path):
+            try:
+                traffic = json.load(open(tr_path)).get(f"{args.workload}:{args.mode}")
+            except Exception:
+                traffic = None
+        state_bytes = ncomp * nloc * 4
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "dtype": "f32" if mode == capi.MODE_FAST else "f32 (+2 f64 islands per cell, bit-exact mode)", "data": "synthetic",
+            "config": {"workload": args.workload, "description": w["desc"], "grid_global": [nx_global, ny],
+                       "grid_per_gpu": [ss.slab.nx_local, ny], "arith_mode": args.mode, "kernel": variant,
+                       "parallelism": f"slab{world}" if world > 1 else "single",
+                       "l2": "inputs larger than L2 (no flush needed)" if state_bytes > L2_BYTES else "state fits in L2 (resident between steps by design)"},
+            "gpu_launches": launches,
+            "e2e": e2e,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel": variant},
+            "clocks": clocks,
+        }
+        if not args.no_e2e:
+            line["config"]["e2e_checksum_rho"] = checksum
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cb = cpu_reference_rate(args.workload)
+                line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")} if cb else None
+            except Exception as ex:  # the baseline is reported context, never a reason to lose the GPU number
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())
