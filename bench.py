@@ -210,6 +210,10 @@ def main():
     ny = (args.ny or w["ny"]) if base.dims == 2 else 1
     nx_global = nx_per * world if w["scaling"] == "weak" else nx_per
     pb = base.resized(nx_global, ny) if base.dims == 2 else base.resized(nx_global)
+    if base.dims == 2:
+        # keep DX == DY (so DT_ON_DX == DT_ON_DY == 0.125 as in every reference run): the domain is [0, nx/ny] x [0, 1]
+        from dataclasses import replace
+        pb = replace(pb, lx=float(nx_global) / float(ny), ly=1.0)
     mode = capi.MODE_STRICT if args.mode == "strict" else capi.MODE_FAST
     K, W = args.steps, args.warmup
 

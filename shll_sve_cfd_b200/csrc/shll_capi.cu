@@ -169,6 +169,9 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     if (g.dims == 2) g.tform = SHLL_TFORM_2D;
     if (!(g.dt_on_dx > 0.0f) || (g.dims == 2 && !(g.dt_on_dy > 0.0f))) return fail(nullptr, SHLL_E_INVAL, "dt_on_dx / dt_on_dy must be positive");
 
+    if ((double)(g.nx + 8) * (double)g.ny >= 2147483647.0)
+        return fail(nullptr, SHLL_E_INVAL, "slab of %d x %d cells exceeds the 32-bit plane index used by the kernels; use more slabs", g.nx, g.ny);
+
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

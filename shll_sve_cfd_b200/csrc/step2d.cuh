@@ -5,15 +5,18 @@
 // reference's layout (base_shll_2d.c:157).  Each plane carries 2 halo rows below row 0 and above row nx-1.
 //
 // Work decomposition -- no shared memory, no __syncthreads, every warp is independent:
-//   * a warp owns a column tile of 32*VEC consecutive j and a chunk of `rows_per_chunk` consecutive i;
+//   * a warp owns a column tile of 32*VEC consecutive j and a chunk of consecutive rows i;
 //   * it marches along i keeping the x-direction stencil (F+ of rows behind, F- of rows ahead, slopes) in a
-//     register sliding window, so each cell's primitives and split fluxes are evaluated once per step
-//     (plus ORDER halo rows per chunk end);
+//     register sliding window of 3 (order 1) or 4 (order 2) row slots whose roles rotate -- the loop is unrolled
+//     by the window depth so no register is ever copied -- and each cell's primitives and split fluxes are
+//     evaluated once per step (plus ORDER halo rows per chunk end);
 //   * the y-direction neighbours (H+ from j-1, H- from j+1, limited slopes) come from the adjacent lanes by
 //     warp shuffle; the outermost HL lanes of the warp are halo lanes that recompute the neighbouring tile's
 //     edge cells, so tiles overlap by 2*HL*VEC columns and nothing crosses a warp;
-//   * lane -> VEC consecutive j, so a warp reads 128*VEC contiguous bytes per plane per row (float/float2/float4 loads);
-//   * the next row's state is prefetched into registers one iteration ahead.
+//   * lane -> VEC consecutive j, so a warp reads 128*VEC contiguous bytes per plane per row (float/float2/float4);
+//   * the next row's state is prefetched into the free `u` registers of the oldest slot one row ahead;
+//   * walls are handled by patching the slot of the non-existent neighbour row (x) or the shuffled-in values (y)
+//     inside warp-uniform branches, so interior warps / rows execute no boundary selects.
 // Algorithmic traffic: 4 planes read + 4 planes written = 32 B per cell per step.
 #pragma once
 #include "halo_sync.cuh"
@@ -76,69 +79,244 @@ __device__ __forceinline__ float wall_flux(float same, float opposite, int k, in
     return same;
 }
 
+// One row of cells as held by a warp: VEC cells per lane.  Members that a given ORDER never touches are never
+// materialised (everything is fully unrolled into registers).
 template <int VEC>
-struct Row2D {
-    float u[VEC][4];
-    float fp[VEC][4], fm[VEC][4];  // x split fluxes F+, F-
-    float sy1[VEC][4];             // hp - hm + Top - Bottom
+struct RowSlot {
+    float u[VEC][4];                 // conserved state (also the landing zone of the prefetch)
+    float fp[VEC][4], fm[VEC][4];    // x split fluxes F+, F-
+    float s1[VEC][4];                // hp - hm + Top - Bottom
+    float s2[VEC][4];                // dhp + dhm - Top_df - Bottom_df          (order 2)
+    float dfp[VEC][4], dfm[VEC][4];  // limited x slopes of F+, F-               (order 2)
+};
+
+// Per-thread, per-launch constants of the y direction.
+template <int VEC>
+struct YEdge {
+    bool tile_has_wall;  // warp-uniform: this column tile contains j == 0 or j == ny-1
+    bool at_lo[VEC], at_hi[VEC];
 };
 
 // Fluxes of one row of cells held by the warp + everything the y direction contributes to their update.
 template <int ORDER, int BC, int LIM, int MODE, int VEC>
-__device__ __forceinline__ void row_compute(const float (&u)[VEC][4], const bool (&at_lo)[VEC], const bool (&at_hi)[VEC],
-                                            float alpha, float (&fp)[VEC][4], float (&fm)[VEC][4],
-                                            float (&sy1)[VEC][4], float (&sy2)[VEC][4])
+__device__ __forceinline__ void row_compute(RowSlot<VEC> &S, const YEdge<VEC> &Y, float alpha)
 {
     const unsigned full = 0xffffffffu;
     float hp[VEC][4], hm[VEC][4];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) cell_flux_2d<MODE>(u[v], fp[v], fm[v], hp[v], hm[v]);
+    for (int v = 0; v < VEC; v++) cell_flux_2d<MODE>(S.u[v], S.fp[v], S.fm[v], hp[v], hm[v]);
 
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        // neighbours across the thread boundary
-        float hp_from_lo = __shfl_up_sync(full, hp[VEC - 1][k], 1);   // H+ of cell j-1
-        float hm_from_hi = __shfl_down_sync(full, hm[0][k], 1);       // H- of cell j+1
-        float hpL[VEC], hmR[VEC];
+        float bottom[VEC], top[VEC];  // H+ of cell j-1, H- of cell j+1
+        const float hp_from_lo = __shfl_up_sync(full, hp[VEC - 1][k], 1);
+        const float hm_from_hi = __shfl_down_sync(full, hm[0][k], 1);
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
-            hpL[v] = (v > 0) ? hp[v > 0 ? v - 1 : 0][k] : hp_from_lo;
-            hmR[v] = (v < VEC - 1) ? hm[v < VEC - 1 ? v + 1 : 0][k] : hm_from_hi;
+            bottom[v] = (v > 0) ? hp[v > 0 ? v - 1 : 0][k] : hp_from_lo;
+            top[v] = (v < VEC - 1) ? hm[v < VEC - 1 ? v + 1 : 0][k] : hm_from_hi;
         }
-#pragma unroll
-        for (int v = 0; v < VEC; v++) {
-            float bottom = at_lo[v] ? wall_flux<BC>(hp[v][k], hm[v][k], k, 2) : hpL[v];
-            float top = at_hi[v] ? wall_flux<BC>(hm[v][k], hp[v][k], k, 2) : hmR[v];
-            sy1[v][k] = flux_sum<MODE>(hp[v][k], hm[v][k], top, bottom);
-        }
+        float dhp[VEC], dhm[VEC];
         if (ORDER == 2) {
-            float hm_from_lo = __shfl_up_sync(full, hm[VEC - 1][k], 1);  // H- of cell j-1
-            float hp_from_hi = __shfl_down_sync(full, hp[0][k], 1);      // H+ of cell j+1
-            float dhp[VEC], dhm[VEC];
+            const float hm_from_lo = __shfl_up_sync(full, hm[VEC - 1][k], 1);
+            const float hp_from_hi = __shfl_down_sync(full, hp[0][k], 1);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {  // 2nd_order_base_shll.c:336-343 (on the un-patched neighbours)
+                const float hmL = (v > 0) ? hm[v > 0 ? v - 1 : 0][k] : hm_from_lo;
+                const float hpR = (v < VEC - 1) ? hp[v < VEC - 1 ? v + 1 : 0][k] : hp_from_hi;
+                dhp[v] = limited_slope<LIM>(bottom[v], hp[v][k], hpR, alpha);
+                dhm[v] = limited_slope<LIM>(hmL, hm[v][k], top[v], alpha);
+            }
+        }
+        if (Y.tile_has_wall) {  // warp-uniform: only the first and last column tile
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
-                float hmL = (v > 0) ? hm[v > 0 ? v - 1 : 0][k] : hm_from_lo;
-                float hpR = (v < VEC - 1) ? hp[v < VEC - 1 ? v + 1 : 0][k] : hp_from_hi;
-                bool edge = at_lo[v] || at_hi[v];  // 2nd_order_base_shll.c:292-300,314-322: first order in wall cells
-                dhp[v] = edge ? 0.0f : limited_slope<LIM>(hpL[v], hp[v][k], hpR, alpha);
-                dhm[v] = edge ? 0.0f : limited_slope<LIM>(hmL, hm[v][k], hmR[v], alpha);
+                if (Y.at_lo[v]) bottom[v] = wall_flux<BC>(hp[v][k], hm[v][k], k, 2);
+                if (Y.at_hi[v]) top[v] = wall_flux<BC>(hm[v][k], hp[v][k], k, 2);
+                if (ORDER == 2) {
+                    if (Y.at_lo[v] || Y.at_hi[v]) dhp[v] = dhm[v] = 0.0f;  // :292-300,314-322
+                }
             }
-            float dhp_from_lo = __shfl_up_sync(full, dhp[VEC - 1], 1);
-            float dhm_from_hi = __shfl_down_sync(full, dhm[0], 1);
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; v++) S.s1[v][k] = flux_sum<MODE>(hp[v][k], hm[v][k], top[v], bottom[v]);
+        if (ORDER == 2) {
+            const float dhp_from_lo = __shfl_up_sync(full, dhp[VEC - 1], 1);
+            const float dhm_from_hi = __shfl_down_sync(full, dhm[0], 1);
+            float bdf[VEC], tdf[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
-                float bdf = (v > 0) ? dhp[v > 0 ? v - 1 : 0] : dhp_from_lo;        // Bottom_df = dhp[j-1]
-                float tdf = (v < VEC - 1) ? dhm[v < VEC - 1 ? v + 1 : 0] : dhm_from_hi;  // Top_df = dhm[j+1]
-                bdf = at_lo[v] ? 0.0f : bdf;  // 2nd_order_base_shll.c:396-399
-                tdf = at_hi[v] ? 0.0f : tdf;  // :412-415
-                sy2[v][k] = slope_sum(dhp[v], dhm[v], tdf, bdf);
+                bdf[v] = (v > 0) ? dhp[v > 0 ? v - 1 : 0] : dhp_from_lo;              // Bottom_df = dhp[j-1]
+                tdf[v] = (v < VEC - 1) ? dhm[v < VEC - 1 ? v + 1 : 0] : dhm_from_hi;  // Top_df = dhm[j+1]
             }
+            if (Y.tile_has_wall) {
+#pragma unroll
+                for (int v = 0; v < VEC; v++) {
+                    if (Y.at_lo[v]) bdf[v] = 0.0f;  // 2nd_order_base_shll.c:396-399
+                    if (Y.at_hi[v]) tdf[v] = 0.0f;  // :412-415
+                }
+            }
+#pragma unroll
+            for (int v = 0; v < VEC; v++) S.s2[v][k] = slope_sum(dhp[v], dhm[v], tdf[v], bdf[v]);
         }
     }
 }
 
+// Everything a warp needs to know about its rows.  All row predicates are reduced to comparisons against a few
+// per-warp integers computed once, and all addressing is 32-bit (plane sizes are checked on the host).
+template <int VEC>
+struct RowCtx {
+    const Step2DParams *P;
+    int ny, r0, r1;
+    int jl, j0;          // clamped load column, own column
+    int rmin, rmax;      // rows that exist in memory: [rmin, rmax]
+    int wall_lo_row;     // 0 if local row 0 is a physical wall, else a row index that never occurs
+    int wall_hi_row;     // nx-1 if local row nx-1 is a physical wall, else never
+    int peer_lo_end;     // rows [0, peer_lo_end) are also stored into the lower neighbour's halo (0 if none)
+    int peer_hi_begin;   // rows [peer_hi_begin, nx) are also stored into the upper neighbour's halo (INT_MAX if none)
+    bool owner;
+    YEdge<VEC> Y;
+
+    __device__ __forceinline__ bool row_exists(int r) const { return r >= rmin && r <= rmax; }
+    __device__ __forceinline__ void load_row(int r, float (&u)[VEC][4]) const
+    {
+        const int idx = r * ny + jl;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float t[VEC];
+            VecIO<VEC>::load(P->in[k] + idx, t);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) u[v][k] = t[v];
+        }
+    }
+    template <int ORDER>
+    __device__ __forceinline__ void store_row(int i, const float (&u)[VEC][4]) const
+    {
+        if (!owner) return;
+        const int idx = i * ny + j0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float t[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) t[v] = u[v][k];
+            VecIO<VEC>::store(P->out[k] + idx, t);
+        }
+        // halo exchange fused into the step: edge rows also go straight into the neighbour GPU's halo rows
+        if (i < peer_lo_end || i >= peer_hi_begin) {
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float t[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; v++) t[v] = u[v][k];
+                if (i < peer_lo_end) VecIO<VEC>::store(P->lo_peer[k] + idx, t);
+                else VecIO<VEC>::store(P->hi_peer[k] + ((i - peer_hi_begin) * ny + j0), t);
+            }
+        }
+    }
+};
+
+// ---- order 1: update row i.  A = row i-1 (F+ valid, u free), B = row i (complete), C = row i+1 (u loaded).
+template <int BC, int LIM, int MODE, int VEC>
+__device__ __forceinline__ void step_o1(const RowCtx<VEC> &X, int i, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C)
+{
+    if (i >= X.r1) return;
+    const Step2DParams &P = *X.P;
+    if (i + 2 <= X.r1 && X.row_exists(i + 2)) X.load_row(i + 2, A.u);  // prefetch one row ahead into the free slot
+    if (X.row_exists(i + 1)) row_compute<1, BC, LIM, MODE, VEC>(C, X.Y, P.alpha);
+    const bool lo = (i == X.wall_lo_row), hi = (i == X.wall_hi_row);
+    if (lo) {  // base_shll_2d.c:152-155 -- the ghost flux replaces the F+ of the non-existent row -1
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) A.fp[v][k] = wall_flux<BC>(B.fp[v][k], B.fm[v][k], k, 1);
+    }
+    if (hi) {  // :168-171
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) C.fm[v][k] = wall_flux<BC>(B.fm[v][k], B.fp[v][k], k, 1);
+    }
+    float uo[VEC][4];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float s = flux_sum<MODE>(B.fp[v][k], B.fm[v][k], C.fm[v][k], A.fp[v][k]);
+            float t = apply_first<MODE>(B.u[v][k], P.dtdx, s);    // base_shll_2d.c:227-230
+            uo[v][k] = apply_first<MODE>(t, P.dtdy, B.s1[v][k]);  // base_shll_2d.c:232-235
+        }
+    }
+    X.template store_row<1>(i, uo);
+}
+
+// ---- order 2: row r arrives in D (u loaded).  A = row r-3 (F+, dF+ valid, u free), B = row r-2 (updated now),
+//      C = row r-1 (its x slopes are computed now), D = row r (fluxes computed now).
+template <int BC, int LIM, int MODE, int VEC, bool POW2>
+__device__ __forceinline__ void step_o2(const RowCtx<VEC> &X, int r, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C,
+                                        RowSlot<VEC> &D)
+{
+    const int rend = X.r1 + 1;
+    if (r > rend) return;
+    const Step2DParams &P = *X.P;
+    if (r + 1 <= rend && X.row_exists(r + 1)) X.load_row(r + 1, A.u);  // prefetch one row ahead
+    if (X.row_exists(r)) row_compute<2, BC, LIM, MODE, VEC>(D, X.Y, P.alpha);
+    {  // limited x slopes of row r-1 (2nd_order_base_shll.c:268-276); first order in wall rows (:226-234,248-256)
+        const int rc = r - 1;
+        const bool wallrow = (rc == X.wall_lo_row) || (rc == X.wall_hi_row);
+        if (wallrow) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++)
+#pragma unroll
+                for (int k = 0; k < 4; k++) C.dfp[v][k] = C.dfm[v][k] = 0.0f;
+        } else {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    C.dfp[v][k] = limited_slope<LIM>(B.fp[v][k], C.fp[v][k], D.fp[v][k], P.alpha);
+                    C.dfm[v][k] = limited_slope<LIM>(B.fm[v][k], C.fm[v][k], D.fm[v][k], P.alpha);
+                }
+            }
+        }
+    }
+    const int i = r - 2;
+    if (i < X.r0) return;  // still filling the window
+    const bool lo = (i == X.wall_lo_row), hi = (i == X.wall_hi_row);
+    if (lo) {  // :216-219 ghost flux, :362-365 Left_df = 0
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                A.fp[v][k] = wall_flux<BC>(B.fp[v][k], B.fm[v][k], k, 1);
+                A.dfp[v][k] = 0.0f;
+            }
+    }
+    if (hi) {  // :243-246, :378-381
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                C.fm[v][k] = wall_flux<BC>(B.fm[v][k], B.fp[v][k], k, 1);
+                C.dfm[v][k] = 0.0f;
+            }
+    }
+    float uo[VEC][4];
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float s = flux_sum<MODE>(B.fp[v][k], B.fm[v][k], C.fm[v][k], A.fp[v][k]);
+            float t = apply_first<MODE>(B.u[v][k], P.dtdx, s);  // :438
+            t = apply_second<MODE, POW2>(t, P.half_dtdx, slope_sum(B.dfp[v][k], B.dfm[v][k], C.dfm[v][k], A.dfp[v][k]));  // :443
+            t = apply_first<MODE>(t, P.dtdy, B.s1[v][k]);                      // :449
+            uo[v][k] = apply_second<MODE, POW2>(t, P.half_dtdy, B.s2[v][k]);   // :454
+        }
+    }
+    X.template store_row<2>(i, uo);
+}
+
 template <int ORDER, int BC, int LIM, int MODE, int VEC, bool POW2>
-__global__ void __launch_bounds__(128) step2d_kernel(const Step2DParams P)
+__global__ void __launch_bounds__(128) step2d_kernel(const __grid_constant__ Step2DParams P)
 {
     constexpr int HL = (ORDER + VEC - 1) / VEC;  // halo lanes per side of the warp tile
     constexpr int USEFUL = (32 - 2 * HL) * VEC;  // columns a warp owns
@@ -149,176 +327,76 @@ __global__ void __launch_bounds__(128) step2d_kernel(const Step2DParams P)
     // chunk order: both edge chunks first (they feed the neighbour GPUs), then the interior
     int chunk = gw / P.ntiles;
     if (P.nchunks > 2) chunk = (chunk == 0) ? 0 : (chunk == 1 ? P.nchunks - 1 : chunk - 1);
-    const int nx = P.nx, ny = P.ny;
-    const int j0 = tile * USEFUL + (lane - HL) * VEC;
-    const int jl = min(max(j0, 0), ny - VEC);  // clamped load column (lanes outside the domain hold unused values)
-    const bool owner = (lane >= HL) && (lane < 32 - HL) && (j0 < ny);
-    bool at_lo[VEC], at_hi[VEC];
+
+    RowCtx<VEC> X;
+    X.P = &P;
+    const int nx = P.nx;
+    X.ny = P.ny;
+    X.j0 = tile * USEFUL + (lane - HL) * VEC;
+    X.jl = min(max(X.j0, 0), X.ny - VEC);  // clamped load column (lanes outside the domain hold unused values)
+    X.owner = (lane >= HL) && (lane < 32 - HL) && (X.j0 < X.ny);
+    X.Y.tile_has_wall = (tile == 0) || (tile == P.ntiles - 1);
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
-        at_lo[v] = (j0 + v == 0);
-        at_hi[v] = (j0 + v == ny - 1);
+        X.Y.at_lo[v] = (X.j0 + v == 0);
+        X.Y.at_hi[v] = (X.j0 + v == X.ny - 1);
     }
-    const int r0 = (int)(((long)chunk * nx) / P.nchunks);
-    const int r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
-    const bool touch_lo = (r0 < ORDER), touch_hi = (r1 > nx - ORDER);
+    X.r0 = (int)(((long)chunk * nx) / P.nchunks);
+    X.r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
+    const int never = -(1 << 30);
+    X.rmin = P.lo_wall ? 0 : -2;
+    X.rmax = P.hi_wall ? nx - 1 : nx + 1;
+    X.wall_lo_row = P.lo_wall ? 0 : never;
+    X.wall_hi_row = P.hi_wall ? nx - 1 : never;
+    X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? ORDER : 0;
+    X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - ORDER : 0x7fffffff;
+    const bool touch_lo = (X.r0 < ORDER), touch_hi = (X.r1 > nx - ORDER);
     if (P.sync.enabled) {  // wait until the neighbour GPUs' edge rows of the previous step sit in our halo rows
         if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
         if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
     }
-    const bool lo_wall = P.lo_wall != 0, hi_wall = P.hi_wall != 0;
-    const float alpha = P.alpha;
-
-    auto row_exists = [&](int r) { return (r >= 0 || !lo_wall) && (r < nx || !hi_wall); };
-    auto load_row = [&](int r, float (&u)[VEC][4]) {
-        const long off = (long)r * ny + jl;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float t[VEC];
-            VecIO<VEC>::load(P.in[k] + off, t);
-#pragma unroll
-            for (int v = 0; v < VEC; v++) u[v][k] = t[v];
-        }
-    };
-    auto store_row = [&](int i, const float (&u)[VEC][4]) {
-        if (!owner) return;
-        const long off = (long)i * ny + j0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float t[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; v++) t[v] = u[v][k];
-            VecIO<VEC>::store(P.out[k] + off, t);
-            // halo exchange fused into the step: edge rows are also stored straight into the neighbour GPU's halo rows
-            if (P.lo_peer[k] != nullptr && i < ORDER) VecIO<VEC>::store(P.lo_peer[k] + (long)i * ny + j0, t);
-            if (P.hi_peer[k] != nullptr && i >= nx - ORDER) VecIO<VEC>::store(P.hi_peer[k] + (long)(i - (nx - ORDER)) * ny + j0, t);
-        }
-    };
 
     if (ORDER == 1) {
-        // window: fpL = F+ of row i-1 ; C = row i ; N = row i+1
-        float fpL[VEC][4];
-        float uC[VEC][4], fpC[VEC][4], fmC[VEC][4], syC[VEC][4], dummy[VEC][4];
-        float uN[VEC][4] = {};
+        RowSlot<VEC> A, B, C;
 #pragma unroll
         for (int v = 0; v < VEC; v++)
 #pragma unroll
-            for (int k = 0; k < 4; k++) fpL[v][k] = 0.0f;
-        if (row_exists(r0 - 1)) {
-            float uL[VEC][4], fmL[VEC][4], syL[VEC][4];
-            load_row(r0 - 1, uL);
-            row_compute<1, BC, LIM, MODE, VEC>(uL, at_lo, at_hi, alpha, fpL, fmL, syL, dummy);
+            for (int k = 0; k < 4; k++) {
+                A.fp[v][k] = 0.0f;
+                C.fm[v][k] = 0.0f;
+                C.u[v][k] = 1.0f;
+            }
+        if (X.row_exists(X.r0 - 1)) {  // F+ of the row below the chunk
+            X.load_row(X.r0 - 1, A.u);
+            row_compute<1, BC, LIM, MODE, VEC>(A, X.Y, P.alpha);
         }
-        load_row(r0, uC);
-        if (row_exists(r0 + 1)) load_row(r0 + 1, uN);
-        row_compute<1, BC, LIM, MODE, VEC>(uC, at_lo, at_hi, alpha, fpC, fmC, syC, dummy);
-
-        for (int i = r0; i < r1; i++) {
-            float uNN[VEC][4] = {};
-            float fpN[VEC][4] = {}, fmN[VEC][4] = {}, syN[VEC][4] = {};
-            const bool have_next = row_exists(i + 1);
-            if (i + 2 <= r1 && row_exists(i + 2)) load_row(i + 2, uNN);  // prefetch one row ahead
-            if (have_next) row_compute<1, BC, LIM, MODE, VEC>(uN, at_lo, at_hi, alpha, fpN, fmN, syN, dummy);
-            const bool lo = (i == 0) && lo_wall, hi = (i == nx - 1) && hi_wall;
-            float uo[VEC][4];
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    float left = lo ? wall_flux<BC>(fpC[v][k], fmC[v][k], k, 1) : fpL[v][k];
-                    float right = hi ? wall_flux<BC>(fmC[v][k], fpC[v][k], k, 1) : fmN[v][k];
-                    float s = flux_sum<MODE>(fpC[v][k], fmC[v][k], right, left);
-                    float t = apply_first<MODE>(uC[v][k], P.dtdx, s);      // base_shll_2d.c:227-230
-                    uo[v][k] = apply_first<MODE>(t, P.dtdy, syC[v][k]);    // base_shll_2d.c:232-235
-                }
-            }
-            store_row(i, uo);
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    fpL[v][k] = fpC[v][k];
-                    fpC[v][k] = fpN[v][k];
-                    fmC[v][k] = fmN[v][k];
-                    syC[v][k] = syN[v][k];
-                    uC[v][k] = uN[v][k];
-                    uN[v][k] = uNN[v][k];
-                }
-            }
+        X.load_row(X.r0, B.u);
+        if (X.row_exists(X.r0 + 1)) X.load_row(X.r0 + 1, C.u);
+        row_compute<1, BC, LIM, MODE, VEC>(B, X.Y, P.alpha);
+        for (int i = X.r0; i < X.r1; i += 3) {  // roles rotate: no register copies
+            step_o1<BC, LIM, MODE, VEC>(X, i, A, B, C);
+            step_o1<BC, LIM, MODE, VEC>(X, i + 1, B, C, A);
+            step_o1<BC, LIM, MODE, VEC>(X, i + 2, C, A, B);
         }
     } else {
-        // window when row r arrives: A = r-3 (F+ and its slope only), B = r-2 (the row being updated),
-        // C = r-1 (slopes computed now), N = r.
-        float fpA[VEC][4], dfpA[VEC][4];
-        float uB[VEC][4], fpB[VEC][4], fmB[VEC][4], dfpB[VEC][4], dfmB[VEC][4], s1B[VEC][4], s2B[VEC][4];
-        float uC[VEC][4], fpC[VEC][4], fmC[VEC][4], s1C[VEC][4], s2C[VEC][4];
-        float uN[VEC][4];
+        RowSlot<VEC> A, B, C, D;
 #pragma unroll
-        for (int v = 0; v < VEC; v++) {
+        for (int v = 0; v < VEC; v++)
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                fpA[v][k] = dfpA[v][k] = 0.0f;
-                uB[v][k] = fpB[v][k] = fmB[v][k] = dfpB[v][k] = dfmB[v][k] = s1B[v][k] = s2B[v][k] = 0.0f;
-                uC[v][k] = fpC[v][k] = fmC[v][k] = s1C[v][k] = s2C[v][k] = 0.0f;
-                uN[v][k] = 1.0f;
+                A.fp[v][k] = A.dfp[v][k] = 0.0f;
+                B.u[v][k] = B.fp[v][k] = B.fm[v][k] = B.dfp[v][k] = B.dfm[v][k] = B.s1[v][k] = B.s2[v][k] = 0.0f;
+                C.u[v][k] = C.fp[v][k] = C.fm[v][k] = C.s1[v][k] = C.s2[v][k] = C.dfp[v][k] = C.dfm[v][k] = 0.0f;
+                D.u[v][k] = 1.0f;
+                D.fp[v][k] = D.fm[v][k] = D.s1[v][k] = D.s2[v][k] = 0.0f;
             }
-        }
-        const int rbeg = r0 - 2, rend = r1 + 1;  // inclusive
-        if (row_exists(rbeg)) load_row(rbeg, uN);
-        for (int r = rbeg; r <= rend; r++) {
-            float uNN[VEC][4] = {};
-            float fpN[VEC][4] = {}, fmN[VEC][4] = {}, s1N[VEC][4] = {}, s2N[VEC][4] = {};
-            if (r + 1 <= rend && row_exists(r + 1)) load_row(r + 1, uNN);  // prefetch one row ahead
-            if (row_exists(r)) row_compute<2, BC, LIM, MODE, VEC>(uN, at_lo, at_hi, alpha, fpN, fmN, s1N, s2N);
-            // limited x slopes of row r-1 (2nd_order_base_shll.c:268-276); first order in wall rows (:226-234,248-256)
-            float dfpC[VEC][4], dfmC[VEC][4];
-            {
-                const int rc = r - 1;
-                const bool wallrow = ((rc == 0) && lo_wall) || ((rc == nx - 1) && hi_wall);
-#pragma unroll
-                for (int v = 0; v < VEC; v++) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        dfpC[v][k] = wallrow ? 0.0f : limited_slope<LIM>(fpB[v][k], fpC[v][k], fpN[v][k], alpha);
-                        dfmC[v][k] = wallrow ? 0.0f : limited_slope<LIM>(fmB[v][k], fmC[v][k], fmN[v][k], alpha);
-                    }
-                }
-            }
-            const int i = r - 2;
-            if (i >= r0) {  // i < r1 by construction
-                const bool lo = (i == 0) && lo_wall, hi = (i == nx - 1) && hi_wall;
-                float uo[VEC][4];
-#pragma unroll
-                for (int v = 0; v < VEC; v++) {
-#pragma unroll
-                    for (int k = 0; k < 4; k++) {
-                        float left = lo ? wall_flux<BC>(fpB[v][k], fmB[v][k], k, 1) : fpA[v][k];
-                        float right = hi ? wall_flux<BC>(fmB[v][k], fpB[v][k], k, 1) : fmC[v][k];
-                        float s = flux_sum<MODE>(fpB[v][k], fmB[v][k], right, left);
-                        float t = apply_first<MODE>(uB[v][k], P.dtdx, s);                 // 2nd_order_base_shll.c:438
-                        float ldf = lo ? 0.0f : dfpA[v][k];                               // :362-365
-                        float rdf = hi ? 0.0f : dfmC[v][k];                               // :378-381
-                        t = apply_second<MODE, POW2>(t, P.half_dtdx, slope_sum(dfpB[v][k], dfmB[v][k], rdf, ldf));  // :443
-                        t = apply_first<MODE>(t, P.dtdy, s1B[v][k]);                      // :449
-                        uo[v][k] = apply_second<MODE, POW2>(t, P.half_dtdy, s2B[v][k]);   // :454
-                    }
-                }
-                store_row(i, uo);
-            }
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    fpA[v][k] = fpB[v][k];
-                    dfpA[v][k] = dfpB[v][k];
-                    uB[v][k] = uC[v][k]; fpB[v][k] = fpC[v][k]; fmB[v][k] = fmC[v][k];
-                    dfpB[v][k] = dfpC[v][k]; dfmB[v][k] = dfmC[v][k];
-                    s1B[v][k] = s1C[v][k]; s2B[v][k] = s2C[v][k];
-                    uC[v][k] = uN[v][k]; fpC[v][k] = fpN[v][k]; fmC[v][k] = fmN[v][k];
-                    s1C[v][k] = s1N[v][k]; s2C[v][k] = s2N[v][k];
-                    uN[v][k] = uNN[v][k];
-                }
-            }
+        const int rbeg = X.r0 - 2;
+        if (X.row_exists(rbeg)) X.load_row(rbeg, D.u);
+        for (int r = rbeg; r <= X.r1 + 1; r += 4) {
+            step_o2<BC, LIM, MODE, VEC, POW2>(X, r, A, B, C, D);
+            step_o2<BC, LIM, MODE, VEC, POW2>(X, r + 1, B, C, D, A);
+            step_o2<BC, LIM, MODE, VEC, POW2>(X, r + 2, C, D, A, B);
+            step_o2<BC, LIM, MODE, VEC, POW2>(X, r + 3, D, A, B, C);
         }
     }
     if (P.sync.enabled) {  // publish: our edge rows of this step have landed in the neighbours' halo rows
