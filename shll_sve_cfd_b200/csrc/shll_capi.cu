@@ -6,6 +6,7 @@
 //           cells.  One cudaMalloc, so that one CUDA-IPC handle exposes both buffers to the neighbour slabs.
 //   flags : halo-arrival flags / edge counters / error word (see halo_sync.cuh).
 // There is no host fallback anywhere in this file: every entry point either runs CUDA work or returns an error.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <unistd.h>
 
@@ -55,6 +56,10 @@ struct shll_ctx {
     unsigned epoch;        // step launches since creation
     KernelKey key;
     int ntiles, nchunks;
+    CUtensorMap tmap[2];   // 2D TMA kernels: one 3D map {ny, nx+4, 4} per ping-pong buffer
+    CUtensorMap *tmap_dev; // the same two descriptors in device memory
+    int tma_stages;
+    size_t tma_smem;
     char variant[128];
     char err[512];
     // neighbours
@@ -105,16 +110,67 @@ void plan_2d(shll_ctx *c)
     int vec = g.variant > 0 ? g.variant : env_int("SHLL_VEC", 0);
     if (vec != 1 && vec != 2 && vec != 4) vec = (g.order == 1) ? 2 : 1;  // defaults from the B200 sweep in DESIGN.md
     while (vec > 1 && (g.ny % vec != 0 || g.ny < 32 * vec)) vec >>= 1;
+    // TMA-fed kernel (step2d_tma.cuh) whenever the row stride is a multiple of 16 bytes; SHLL_TMA=0 forces the LDG kernel.
+    c->key.tma = (g.ny % 4 == 0) && (g.ny >= 32) && env_int("SHLL_TMA", 1) != 0;
+    if (c->key.tma) {
+        const int maxvec = (g.order == 1) ? 2 : 1;  // instantiated TMA widths
+        if (g.variant <= 0 && env_int("SHLL_VEC", 0) <= 0) vec = 1;
+        if (vec > maxvec) vec = maxvec;
+    }
     c->key.vec = vec;
     const int hl = (g.order + vec - 1) / vec;
     const int useful = (32 - 2 * hl) * vec;
     c->ntiles = (g.ny + useful - 1) / useful;
-    int rpc = env_int("SHLL_ROWS_PER_CHUNK", 64);
+    int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? 48 : 64);
     if (rpc < 2) rpc = 2;
     int nchunks = (g.nx + rpc - 1) / rpc;
     if (nchunks < 1) nchunks = 1;
     while (nchunks > 1 && g.nx / nchunks < 2) nchunks--;
     c->nchunks = nchunks;
+}
+
+typedef CUresult (*encode_tiled_fn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 3D tensor maps {ny, nx+4, 4 planes} over each ping-pong buffer, origin at halo row -2 of plane 0; box = the warp's
+// 32*vec columns x R rows x 4 planes.  The driver entry point is looked up at run time (no link dependency on libcuda).
+int make_tensor_maps(shll_ctx *c)
+{
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess) return -1;
+    const shll_config &g = c->cfg;
+    const int R = (g.order == 1) ? 3 : 4;
+    for (int b = 0; b < 2; b++) {
+        float *base = c->state + (size_t)b * c->ncomp * c->plane_elems;  // plane 0, halo row -2
+        cuuint64_t dims[3] = {(cuuint64_t)g.ny, (cuuint64_t)(g.nx + 4), 4};
+        cuuint64_t strides[2] = {(cuuint64_t)g.ny * 4, (cuuint64_t)c->plane_elems * 4};
+        cuuint32_t box[3] = {(cuuint32_t)(32 * c->key.vec + 4), (cuuint32_t)R, 4};  // 4 spare columns: 16-byte aligned box start
+        cuuint32_t estr[3] = {1, 1, 1};
+        CUresult r = ((encode_tiled_fn)fn)(&c->tmap[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, box, estr,
+                                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                           CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) return -(int)r - 100;
+    }
+    if (env_int("SHLL_TMAP_GLOBAL", 0)) {
+        if (cudaMalloc(&c->tmap_dev, 2 * sizeof(CUtensorMap)) != cudaSuccess) return -2;
+        if (cudaMemcpy(c->tmap_dev, c->tmap, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
+    }
+    c->tma_stages = env_int("SHLL_TMA_STAGES", 4);
+    if (c->tma_stages < 2) c->tma_stages = 2;
+    if (c->tma_stages > 16) c->tma_stages = 16;
+    const size_t stage_stride = ((size_t)4 * R * (32 * c->key.vec + 4) * 4 + 127) & ~(size_t)127;
+    c->tma_smem = (size_t)c->tma_stages * stage_stride + 8 * c->tma_stages;
+    return 0;
+}
+
+void plan_2d_fallback(shll_ctx *c)
+{
+    setenv("SHLL_TMA", "0", 1);
+    plan_2d(c);
+    unsetenv("SHLL_TMA");
 }
 
 void plan_1d(shll_ctx *c)
@@ -225,6 +281,16 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     fill_kernel<<<1024, 256, 0, c->stream>>>(c->state, 1.0f, state_bytes / sizeof(float));
     CKC(cudaGetLastError());
     CKC(cudaStreamSynchronize(c->stream));
+    if (g.dims == 2 && c->key.tma) {
+        int rc = make_tensor_maps(c);
+        if (rc != 0) {  // not fatal: the LDG kernel computes the same bits
+            c->key.tma = false;
+            plan_2d_fallback(c);
+        }
+    }
+    snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? "_tma" : "",
+             g.order, g.bc == SHLL_BC_REFLECT ? "reflect" : "outflow", g.order == 2 ? (g.limiter == SHLL_LIM_MC ? "mc_" : "minmod_") : "",
+             g.mode == SHLL_MODE_STRICT ? "strict" : "fast", c->key.pow2 ? "pow2" : "gendt", c->key.vec, c->ntiles, c->nchunks);
 #undef CKC
     *out = c;
     return SHLL_OK;
@@ -242,6 +308,7 @@ int shll_destroy(shll_ctx *c)
         }
     }
     if (c->scratch) cudaFree(c->scratch);
+    if (c->tmap_dev) cudaFree(c->tmap_dev);
     if (c->state) cudaFree(c->state);
     if (c->flags) cudaFree(c->flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -347,10 +414,22 @@ int launch_one_step(shll_ctx *c)
         S.edge_warps_lo = S.edge_warps_hi = (unsigned)c->ntiles;
         P.sync = S;
         const int warps = c->ntiles * c->nchunks;
-        dim3 block(128), grid((warps + 3) / 4);
-        if (g.order == 1) e = launch_step2d_o1(c->key, P, grid, block, c->stream);
-        else if (g.mode == SHLL_MODE_STRICT) e = launch_step2d_o2_strict(c->key, P, grid, block, c->stream);
-        else e = launch_step2d_o2_fast(c->key, P, grid, block, c->stream);
+        if (c->key.tma) {
+            Step2DTmaParams T;
+            T.base = P;
+            T.tmap = c->tmap[in];
+            T.tmap_global = c->tmap_dev ? c->tmap_dev + in : nullptr;
+            T.stages = c->tma_stages;
+            dim3 grid(warps);
+            if (g.order == 1) e = launch_step2d_tma_o1(c->key, T, grid, c->tma_smem, c->stream);
+            else if (g.mode == SHLL_MODE_STRICT) e = launch_step2d_tma_o2_strict(c->key, T, grid, c->tma_smem, c->stream);
+            else e = launch_step2d_tma_o2_fast(c->key, T, grid, c->tma_smem, c->stream);
+        } else {
+            dim3 block(128), grid((warps + 3) / 4);
+            if (g.order == 1) e = launch_step2d_o1(c->key, P, grid, block, c->stream);
+            else if (g.mode == SHLL_MODE_STRICT) e = launch_step2d_o2_strict(c->key, P, grid, block, c->stream);
+            else e = launch_step2d_o2_fast(c->key, P, grid, block, c->stream);
+        }
     } else {
         Step1DParams P;
         memset(&P, 0, sizeof(P));

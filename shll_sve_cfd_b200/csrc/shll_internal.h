@@ -4,18 +4,23 @@
 
 #include "step1d.cuh"
 #include "step2d.cuh"
+#include "step2d_tma.cuh"
 
 namespace shll {
 
 struct KernelKey {
     int order, bc, lim, mode, vec, tform;
     bool pow2;
+    bool tma;  // 2D only: TMA-fed kernel (needs ny % 4 == 0)
 };
 
 // Each returns cudaSuccess / the launch error; cudaErrorInvalidValue for a combination that was not instantiated.
 cudaError_t launch_step2d_o1(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);
 cudaError_t launch_step2d_o2_strict(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);
 cudaError_t launch_step2d_o2_fast(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);
+cudaError_t launch_step2d_tma_o1(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
+cudaError_t launch_step2d_tma_o2_strict(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
+cudaError_t launch_step2d_tma_o2_fast(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s);
 
 // Compute_P_from_U on the device (for shll_download_p) and the diagnostic CFL reduction.

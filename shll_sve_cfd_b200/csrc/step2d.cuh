@@ -215,22 +215,19 @@ struct RowCtx {
     }
 };
 
-// ---- order 1: update row i.  A = row i-1 (F+ valid, u free), B = row i (complete), C = row i+1 (u loaded).
-template <int BC, int LIM, int MODE, int VEC>
-__device__ __forceinline__ void step_o1(const RowCtx<VEC> &X, int i, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C)
+// ---- order 1: finish row i.  A = row i-1 (F+ valid), B = row i (complete), C = row i+1 (fluxes just computed).
+// X supplies the wall rows and the store (RowCtx for the LDG kernel, TmaCtx for the TMA kernel).
+template <int BC, int MODE, int VEC, class Ctx>
+__device__ __forceinline__ void finish_o1(const Ctx &X, int i, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C)
 {
-    if (i >= X.r1) return;
     const Step2DParams &P = *X.P;
-    if (i + 2 <= X.r1 && X.row_exists(i + 2)) X.load_row(i + 2, A.u);  // prefetch one row ahead into the free slot
-    if (X.row_exists(i + 1)) row_compute<1, BC, LIM, MODE, VEC>(C, X.Y, P.alpha);
-    const bool lo = (i == X.wall_lo_row), hi = (i == X.wall_hi_row);
-    if (lo) {  // base_shll_2d.c:152-155 -- the ghost flux replaces the F+ of the non-existent row -1
+    if (i == X.wall_lo_row) {  // base_shll_2d.c:152-155 -- the ghost flux replaces the F+ of the non-existent row -1
 #pragma unroll
         for (int v = 0; v < VEC; v++)
 #pragma unroll
             for (int k = 0; k < 4; k++) A.fp[v][k] = wall_flux<BC>(B.fp[v][k], B.fm[v][k], k, 1);
     }
-    if (hi) {  // :168-171
+    if (i == X.wall_hi_row) {  // :168-171
 #pragma unroll
         for (int v = 0; v < VEC; v++)
 #pragma unroll
@@ -249,21 +246,16 @@ __device__ __forceinline__ void step_o1(const RowCtx<VEC> &X, int i, RowSlot<VEC
     X.template store_row<1>(i, uo);
 }
 
-// ---- order 2: row r arrives in D (u loaded).  A = row r-3 (F+, dF+ valid, u free), B = row r-2 (updated now),
-//      C = row r-1 (its x slopes are computed now), D = row r (fluxes computed now).
-template <int BC, int LIM, int MODE, int VEC, bool POW2>
-__device__ __forceinline__ void step_o2(const RowCtx<VEC> &X, int r, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C,
-                                        RowSlot<VEC> &D)
+// ---- order 2: row r has just been computed into D.  A = row r-3 (F+, dF+ valid), B = row r-2 (finished now),
+//      C = row r-1 (its x slopes are computed here).
+template <int BC, int LIM, int MODE, int VEC, bool POW2, class Ctx>
+__device__ __forceinline__ void finish_o2(const Ctx &X, int r, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C,
+                                          RowSlot<VEC> &D)
 {
-    const int rend = X.r1 + 1;
-    if (r > rend) return;
     const Step2DParams &P = *X.P;
-    if (r + 1 <= rend && X.row_exists(r + 1)) X.load_row(r + 1, A.u);  // prefetch one row ahead
-    if (X.row_exists(r)) row_compute<2, BC, LIM, MODE, VEC>(D, X.Y, P.alpha);
     {  // limited x slopes of row r-1 (2nd_order_base_shll.c:268-276); first order in wall rows (:226-234,248-256)
         const int rc = r - 1;
-        const bool wallrow = (rc == X.wall_lo_row) || (rc == X.wall_hi_row);
-        if (wallrow) {
+        if ((rc == X.wall_lo_row) || (rc == X.wall_hi_row)) {
 #pragma unroll
             for (int v = 0; v < VEC; v++)
 #pragma unroll
@@ -281,8 +273,7 @@ __device__ __forceinline__ void step_o2(const RowCtx<VEC> &X, int r, RowSlot<VEC
     }
     const int i = r - 2;
     if (i < X.r0) return;  // still filling the window
-    const bool lo = (i == X.wall_lo_row), hi = (i == X.wall_hi_row);
-    if (lo) {  // :216-219 ghost flux, :362-365 Left_df = 0
+    if (i == X.wall_lo_row) {  // :216-219 ghost flux, :362-365 Left_df = 0
 #pragma unroll
         for (int v = 0; v < VEC; v++)
 #pragma unroll
@@ -291,7 +282,7 @@ __device__ __forceinline__ void step_o2(const RowCtx<VEC> &X, int r, RowSlot<VEC
                 A.dfp[v][k] = 0.0f;
             }
     }
-    if (hi) {  // :243-246, :378-381
+    if (i == X.wall_hi_row) {  // :243-246, :378-381
 #pragma unroll
         for (int v = 0; v < VEC; v++)
 #pragma unroll
@@ -308,11 +299,32 @@ __device__ __forceinline__ void step_o2(const RowCtx<VEC> &X, int r, RowSlot<VEC
             float s = flux_sum<MODE>(B.fp[v][k], B.fm[v][k], C.fm[v][k], A.fp[v][k]);
             float t = apply_first<MODE>(B.u[v][k], P.dtdx, s);  // :438
             t = apply_second<MODE, POW2>(t, P.half_dtdx, slope_sum(B.dfp[v][k], B.dfm[v][k], C.dfm[v][k], A.dfp[v][k]));  // :443
-            t = apply_first<MODE>(t, P.dtdy, B.s1[v][k]);                      // :449
-            uo[v][k] = apply_second<MODE, POW2>(t, P.half_dtdy, B.s2[v][k]);   // :454
+            t = apply_first<MODE>(t, P.dtdy, B.s1[v][k]);                     // :449
+            uo[v][k] = apply_second<MODE, POW2>(t, P.half_dtdy, B.s2[v][k]);  // :454
         }
     }
     X.template store_row<2>(i, uo);
+}
+
+// LDG kernel steps: prefetch one row ahead into the oldest slot's free `u` registers, compute, finish.
+template <int BC, int LIM, int MODE, int VEC>
+__device__ __forceinline__ void step_o1(const RowCtx<VEC> &X, int i, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C)
+{
+    if (i >= X.r1) return;
+    if (i + 2 <= X.r1 && X.row_exists(i + 2)) X.load_row(i + 2, A.u);
+    if (X.row_exists(i + 1)) row_compute<1, BC, LIM, MODE, VEC>(C, X.Y, X.P->alpha);
+    finish_o1<BC, MODE, VEC>(X, i, A, B, C);
+}
+
+template <int BC, int LIM, int MODE, int VEC, bool POW2>
+__device__ __forceinline__ void step_o2(const RowCtx<VEC> &X, int r, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C,
+                                        RowSlot<VEC> &D)
+{
+    const int rend = X.r1 + 1;
+    if (r > rend) return;
+    if (r + 1 <= rend && X.row_exists(r + 1)) X.load_row(r + 1, A.u);
+    if (X.row_exists(r)) row_compute<2, BC, LIM, MODE, VEC>(D, X.Y, X.P->alpha);
+    finish_o2<BC, LIM, MODE, VEC, POW2>(X, r, A, B, C, D);
 }
 
 template <int ORDER, int BC, int LIM, int MODE, int VEC, bool POW2>

@@ -1,4 +1,4 @@
-// step2d_o1.cu -- instantiations of the fused 2D step kernel, first order (base_shll_2d.c).
+// step2d_o1.cu -- instantiations of the fused 2D step kernels, first order (base_shll_2d.c): LDG and TMA variants.
 #include "shll_internal.h"
 
 namespace shll {
@@ -7,6 +7,12 @@ template <int BC, int MODE, int VEC>
 static cudaError_t go(const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s)
 {
     step2d_kernel<1, BC, LIM_MINMOD, MODE, VEC, true><<<grid, block, 0, s>>>(p);
+    return cudaGetLastError();
+}
+template <int BC, int MODE, int VEC>
+static cudaError_t go_tma(const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
+{
+    step2d_tma_kernel<1, BC, LIM_MINMOD, MODE, VEC, true><<<grid, 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
@@ -20,6 +26,15 @@ static cudaError_t by_vec(int vec, const Step2DParams &p, dim3 grid, dim3 block,
     }
     return cudaErrorInvalidValue;
 }
+template <int BC, int MODE>
+static cudaError_t by_vec_tma(int vec, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
+{
+    switch (vec) {
+    case 1: return go_tma<BC, MODE, 1>(p, grid, smem, s);
+    case 2: return go_tma<BC, MODE, 2>(p, grid, smem, s);
+    }
+    return cudaErrorInvalidValue;
+}
 
 cudaError_t launch_step2d_o1(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s)
 {
@@ -27,6 +42,15 @@ cudaError_t launch_step2d_o1(const KernelKey &k, const Step2DParams &p, dim3 gri
     if (k.bc == BC_REFLECT && k.mode == MODE_FAST) return by_vec<BC_REFLECT, MODE_FAST>(k.vec, p, grid, block, s);
     if (k.bc == BC_OUTFLOW && k.mode == MODE_STRICT) return by_vec<BC_OUTFLOW, MODE_STRICT>(k.vec, p, grid, block, s);
     if (k.bc == BC_OUTFLOW && k.mode == MODE_FAST) return by_vec<BC_OUTFLOW, MODE_FAST>(k.vec, p, grid, block, s);
+    return cudaErrorInvalidValue;
+}
+
+cudaError_t launch_step2d_tma_o1(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
+{
+    if (k.bc == BC_REFLECT && k.mode == MODE_STRICT) return by_vec_tma<BC_REFLECT, MODE_STRICT>(k.vec, p, grid, smem, s);
+    if (k.bc == BC_REFLECT && k.mode == MODE_FAST) return by_vec_tma<BC_REFLECT, MODE_FAST>(k.vec, p, grid, smem, s);
+    if (k.bc == BC_OUTFLOW && k.mode == MODE_STRICT) return by_vec_tma<BC_OUTFLOW, MODE_STRICT>(k.vec, p, grid, smem, s);
+    if (k.bc == BC_OUTFLOW && k.mode == MODE_FAST) return by_vec_tma<BC_OUTFLOW, MODE_FAST>(k.vec, p, grid, smem, s);
     return cudaErrorInvalidValue;
 }
 

@@ -1,0 +1,294 @@
+// step2d_tma.cuh -- the TMA-fed variant of the fused 2D step kernel (same arithmetic, same register sliding window
+// as step2d.cuh; only the way the state reaches the registers differs).
+//
+// Why: the LDG kernel keeps one row per warp in flight (~10 KB per SM), far below the ~35 KB per SM that Little's law
+// asks for at HBM3e bandwidth x latency, and spends ~10 issue slots per row on address arithmetic.  Here every block is
+// ONE warp with a private shared-memory ring of STAGES boxes; each box is R rows x 32*VEC columns x 4 planes, fetched by
+// ONE `cp.async.bulk.tensor.3d` (TMA) copy issued by one lane and tracked by an mbarrier.  The warp reads its cells
+// back with conflict-free LDS at constant offsets, so loads cost no address arithmetic, (STAGES-1)*R rows per warp are
+// in flight, and out-of-domain halo lanes are zero-filled by the TMA unit instead of being clamped by hand.
+// With one warp per block the tile / chunk / row bookkeeping is warp-uniform by construction and runs on the uniform
+// datapath (no convergence barriers around the row predicates).
+//
+// R equals the unroll factor of the row loop (3 for order 1, 4 for order 2), which makes the row-within-box index a
+// compile-time constant of each unrolled step.
+//
+// TMA alignment: global strides AND the first column of a box must be multiples of 16 bytes (a box starting at column -1
+// traps with "illegal instruction" -- measured with tools/tma_selftest.cu).  The warp tile starts at column
+// tile*USEFUL - HL*VEC, which is only 2- or 1-column aligned, so the box is 4 columns wider than the warp (32*VEC + 4),
+// starts at that column rounded down to a multiple of 4, and each lane adds the 0..3 column remainder to its LDS address.
+// Requires ny % 4 == 0; other shapes use the LDG kernel.
+#pragma once
+#include <cuda.h>
+
+#include "step2d.cuh"
+
+namespace shll {
+
+struct Step2DTmaParams {
+    Step2DParams base;
+    CUtensorMap tmap;     // INPUT buffer as a 3D tensor {ny, nx+4, 4 planes}, origin = halo row -2 of plane 0
+    const CUtensorMap *tmap_global;  // optional copy of the same descriptor in device memory (debug switch SHLL_TMAP_GLOBAL)
+    int stages;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SHLL_WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SHLL_DONE_%=;\n"
+        "bra SHLL_WAIT_%=;\n"
+        "SHLL_DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
+        : "memory");
+}
+
+// Row source + store sink of one warp for the TMA kernel.
+template <int VEC, int R>
+struct TmaCtx {
+    const Step2DParams *P;
+    const Step2DTmaParams *T;
+    int ny, r0, r1, j0;
+    int wall_lo_row, wall_hi_row, peer_lo_end, peer_hi_begin;
+    bool owner;
+    YEdge<VEC> Y;
+    // ring
+    uint32_t ring;       // shared address of stage 0
+    uint32_t bars;       // shared address of mbarrier 0
+    uint32_t lane_off;   // byte offset of this lane's first cell inside a box row
+    int x0;              // first column of the warp's box: multiple of 4 (may be negative: zero-filled)
+    int ybase;           // tensor row of box 0 = rbeg + 2
+    int nboxes;          // boxes this warp consumes
+    int stages;
+    static constexpr uint32_t BOX_COLS = 32 * VEC + 4;
+    static constexpr uint32_t ROW_BYTES = BOX_COLS * 4;
+    static constexpr uint32_t PLANE_BYTES = R * ROW_BYTES;
+    static constexpr uint32_t STAGE_BYTES = 4 * PLANE_BYTES;                 // bytes one box delivers
+    static constexpr uint32_t STAGE_STRIDE = (STAGE_BYTES + 127u) & ~127u;   // TMA destinations are 128-byte aligned
+
+    __device__ __forceinline__ void arm(int box, int stage) const
+    {   // one lane: expect the bytes of the box, then launch ONE 3D copy (32*VEC columns x R rows x 4 planes)
+        const uint32_t bar = bars + 8u * stage;
+        mbar_expect_tx(bar, STAGE_BYTES);
+        tma_load_3d(ring + STAGE_STRIDE * stage, T->tmap_global ? T->tmap_global : &T->tmap, x0, ybase + box * R, 0, bar);
+    }
+    // TMA zero-fills cells outside the domain; a zero density would send those (unused) lanes through the IEEE slow
+    // paths of every divide and drag the whole warp: give them a benign gas state instead.  First/last column tile only.
+    __device__ __forceinline__ void sanitize(float (&u)[VEC][4]) const
+    {
+        if (Y.tile_has_wall) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                const bool outside = (j0 + v < 0) || (j0 + v >= ny);
+#pragma unroll
+                for (int k = 0; k < 4; k++) u[v][k] = outside ? 1.0f : u[v][k];
+            }
+        }
+    }
+    // read row `within` of the box sitting in `stage`
+    template <int WITHIN>
+    __device__ __forceinline__ void read_row(int stage, float (&u)[VEC][4]) const
+    {
+        const uint32_t a = ring + STAGE_STRIDE * stage + WITHIN * ROW_BYTES + lane_off;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            if (VEC == 1) {
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(u[0][k]) : "r"(a + k * PLANE_BYTES));
+            } else if (VEC == 2) {
+                asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(u[0][k]), "=f"(u[VEC > 1 ? 1 : 0][k]) : "r"(a + k * PLANE_BYTES));
+            } else {
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(u[0][k]), "=f"(u[VEC > 1 ? 1 : 0][k]), "=f"(u[VEC > 2 ? 2 : 0][k]), "=f"(u[VEC > 3 ? 3 : 0][k])
+                             : "r"(a + k * PLANE_BYTES));
+            }
+        }
+        sanitize(u);
+    }
+    template <int ORDER>
+    __device__ __forceinline__ void store_row(int i, const float (&u)[VEC][4]) const
+    {
+        if (!owner) return;
+        const int idx = i * ny + j0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            float t[VEC];
+#pragma unroll
+            for (int v = 0; v < VEC; v++) t[v] = u[v][k];
+            VecIO<VEC>::store(P->out[k] + idx, t);
+        }
+        if (i < peer_lo_end || i >= peer_hi_begin) {  // halo exchange fused into the step (multi-GPU edge rows)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                float t[VEC];
+#pragma unroll
+                for (int v = 0; v < VEC; v++) t[v] = u[v][k];
+                if (i < peer_lo_end) VecIO<VEC>::store(P->lo_peer[k] + idx, t);
+                else VecIO<VEC>::store(P->hi_peer[k] + ((i - peer_hi_begin) * ny + j0), t);
+            }
+        }
+    }
+};
+
+template <int ORDER, int BC, int LIM, int MODE, int VEC, bool POW2>
+__global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ Step2DTmaParams T)
+{
+    constexpr int R = (ORDER == 1) ? 3 : 4;      // rows per box == unroll factor of the row loop
+    constexpr int HL = (ORDER + VEC - 1) / VEC;  // halo lanes per side of the warp tile
+    constexpr int USEFUL = (32 - 2 * HL) * VEC;  // columns a warp owns
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Step2DParams &P = T.base;
+    const int lane = threadIdx.x;
+    const int gw = blockIdx.x;  // one warp per block: everything derived from it is warp-uniform
+    const int tile = gw % P.ntiles;
+    int chunk = gw / P.ntiles;
+    if (P.nchunks > 2) chunk = (chunk == 0) ? 0 : (chunk == 1 ? P.nchunks - 1 : chunk - 1);  // edge chunks first
+
+    TmaCtx<VEC, R> X;
+    X.P = &P;
+    X.T = &T;
+    const int nx = P.nx;
+    X.ny = P.ny;
+    const int xs = tile * USEFUL - HL * VEC;  // first column of the warp tile (halo lanes included)
+    X.x0 = xs & ~3;                           // box start, 16-byte aligned (floor, also for negative xs)
+    X.j0 = xs + lane * VEC;
+    X.owner = (lane >= HL) && (lane < 32 - HL) && (X.j0 < X.ny);
+    X.Y.tile_has_wall = (tile == 0) || (tile == P.ntiles - 1);
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        X.Y.at_lo[v] = (X.j0 + v == 0);
+        X.Y.at_hi[v] = (X.j0 + v == X.ny - 1);
+    }
+    X.r0 = (int)(((long)chunk * nx) / P.nchunks);
+    X.r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
+    const int never = -(1 << 30);
+    X.wall_lo_row = P.lo_wall ? 0 : never;
+    X.wall_hi_row = P.hi_wall ? nx - 1 : never;
+    X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? ORDER : 0;
+    X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - ORDER : 0x7fffffff;
+    const int rmax = P.hi_wall ? nx - 1 : nx + 1;  // last row that exists in memory
+    const int rmin = P.lo_wall ? 0 : -2;
+    const bool touch_lo = (X.r0 < ORDER), touch_hi = (X.r1 > nx - ORDER);
+    if (P.sync.enabled) {  // the neighbour GPUs' edge rows of the previous step must sit in our halo rows
+        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
+        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
+    }
+
+    // ---- ring set-up
+    const int rbeg = X.r0 - ORDER;  // first row the warp consumes (may not exist at a wall: its box is still fetched)
+    const int rlast = X.r1 - 1 + ORDER;
+    X.stages = T.stages;
+    X.ring = smem_u32(smem);
+    X.bars = X.ring + TmaCtx<VEC, R>::STAGE_STRIDE * X.stages;
+    X.lane_off = (uint32_t)(xs - X.x0 + lane * VEC) * 4u;
+    X.ybase = rbeg + 2;
+    X.nboxes = (rlast - rbeg) / R + 1;
+    if (lane == 0) {
+        for (int s = 0; s < X.stages; s++) mbar_init(X.bars + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int b = 0; b < X.stages && b < X.nboxes; b++) X.arm(b, b);
+    }
+    __syncwarp();
+
+    int stage = 0;        // stage holding the box currently being consumed
+    uint32_t parity = 0;  // its mbarrier phase
+    int box = 0;
+    auto next_box = [&]() {  // the box in `stage` has been fully read: refill it, move on
+        __syncwarp();
+        if (lane == 0 && box + X.stages < X.nboxes) X.arm(box + X.stages, stage);
+        box++;
+        stage++;
+        if (stage == X.stages) { stage = 0; parity ^= 1u; }
+    };
+
+    if (ORDER == 1) {
+        // rows: n = r - rbeg;  box = n / 3, within = n % 3.  Prologue reads n = 0 (row r0-1) and n = 1 (row r0);
+        // the step for row i = r0 + 3m + p reads row i+1, i.e. n = 3m + p + 2: within = 2, 0, 1 for p = 0, 1, 2.
+        RowSlot<VEC> A, B, C;
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) A.fp[v][k] = C.fm[v][k] = 0.0f;
+        mbar_wait(X.bars + 8u * stage, parity);
+        X.template read_row<0>(stage, A.u);
+        X.template read_row<1>(stage, B.u);
+        if (rbeg >= rmin) row_compute<1, BC, LIM, MODE, VEC>(A, X.Y, P.alpha);
+        row_compute<1, BC, LIM, MODE, VEC>(B, X.Y, P.alpha);
+        for (int i = X.r0; i < X.r1; i += 3) {
+            // p = 0: row i+1 is the last row of the current box
+            X.template read_row<2>(stage, C.u);
+            if (i + 1 <= rmax) row_compute<1, BC, LIM, MODE, VEC>(C, X.Y, P.alpha);
+            finish_o1<BC, MODE, VEC>(X, i, A, B, C);
+            next_box();
+            if (i + 1 >= X.r1) break;
+            // p = 1: first row of the next box
+            mbar_wait(X.bars + 8u * stage, parity);
+            X.template read_row<0>(stage, A.u);
+            if (i + 2 <= rmax) row_compute<1, BC, LIM, MODE, VEC>(A, X.Y, P.alpha);
+            finish_o1<BC, MODE, VEC>(X, i + 1, B, C, A);
+            if (i + 2 >= X.r1) break;
+            // p = 2
+            X.template read_row<1>(stage, B.u);
+            if (i + 3 <= rmax) row_compute<1, BC, LIM, MODE, VEC>(B, X.Y, P.alpha);
+            finish_o1<BC, MODE, VEC>(X, i + 2, C, A, B);
+        }
+    } else {
+        // rows: the step at unrolled position p of iteration m handles row r = rbeg + 4m + p: box m, within p.
+        RowSlot<VEC> A, B, C, D;
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                A.fp[v][k] = A.dfp[v][k] = 0.0f;
+                B.u[v][k] = B.fp[v][k] = B.fm[v][k] = B.dfp[v][k] = B.dfm[v][k] = B.s1[v][k] = B.s2[v][k] = 0.0f;
+                C.u[v][k] = C.fp[v][k] = C.fm[v][k] = C.s1[v][k] = C.s2[v][k] = C.dfp[v][k] = C.dfm[v][k] = 0.0f;
+                D.fp[v][k] = D.fm[v][k] = D.s1[v][k] = D.s2[v][k] = 0.0f;
+            }
+        for (int r = rbeg; r <= rlast; r += 4) {
+            mbar_wait(X.bars + 8u * stage, parity);
+            X.template read_row<0>(stage, D.u);
+            if (r >= rmin && r <= rmax) row_compute<2, BC, LIM, MODE, VEC>(D, X.Y, P.alpha);
+            finish_o2<BC, LIM, MODE, VEC, POW2>(X, r, A, B, C, D);
+            if (r + 1 > rlast) break;
+            X.template read_row<1>(stage, A.u);
+            if (r + 1 >= rmin && r + 1 <= rmax) row_compute<2, BC, LIM, MODE, VEC>(A, X.Y, P.alpha);
+            finish_o2<BC, LIM, MODE, VEC, POW2>(X, r + 1, B, C, D, A);
+            if (r + 2 > rlast) break;
+            X.template read_row<2>(stage, B.u);
+            if (r + 2 >= rmin && r + 2 <= rmax) row_compute<2, BC, LIM, MODE, VEC>(B, X.Y, P.alpha);
+            finish_o2<BC, LIM, MODE, VEC, POW2>(X, r + 2, C, D, A, B);
+            if (r + 3 > rlast) break;
+            X.template read_row<3>(stage, C.u);
+            if (r + 3 >= rmin && r + 3 <= rmax) row_compute<2, BC, LIM, MODE, VEC>(C, X.Y, P.alpha);
+            finish_o2<BC, LIM, MODE, VEC, POW2>(X, r + 3, D, A, B, C);
+            next_box();
+        }
+    }
+    if (P.sync.enabled) {  // publish: our edge rows of this step have landed in the neighbours' halo rows
+        if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);
+        if (touch_hi) halo_arrive(P.sync, P.sync.cnt_hi, P.sync.edge_warps_hi, P.sync.sig_hi);
+    }
+}
+
+}  // namespace shll

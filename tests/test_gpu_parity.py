@@ -4,6 +4,8 @@ STRICT mode must be bit-exact (0 ULP) on every conserved component.  FAST mode m
 BASELINE.md / SURVEY.md App. A on the parity configs: |x - ref| <= 3e-5 + 3e-5*|ref| on every primitive field.
 Nothing here reads /root/reference: the fixtures are committed, the oracle is built from oracle/shll_oracle.c.
 """
+from dataclasses import replace
+
 import numpy as np
 import pytest
 
@@ -122,21 +124,40 @@ def test_1d_ragged_sizes(n, order, oracle):
 @pytest.mark.parametrize("order", [1, 2])
 def test_2d_ragged_sizes(shape, order, oracle):
     pb = (programs.BASE_SHLL_2D if order == 1 else programs.SECOND_ORDER_2D).resized(*shape)
+    pb = replace(pb, lx=shape[0] / shape[1])   # DX == DY, so DT_ON_DY == 0.125 and the scheme stays stable
     u0 = _random_state(pb, seed=shape[0] * 1000 + shape[1])
     got, ref, name = _gpu_vs_oracle(pb, oracle, u0, 7)
     assert np.array_equal(bits(got), bits(ref)), f"{shape} order={order} {name}"
 
 
+@pytest.mark.parametrize("tma", [0, 1])
 @pytest.mark.parametrize("vec", [1, 2, 4])
 @pytest.mark.parametrize("order", [1, 2])
-def test_2d_every_vector_width_gives_the_same_bits(vec, order, oracle):
-    if order == 2 and vec == 4:
-        pytest.skip("order-2 kernel is instantiated for 1 and 2 cells per thread")
-    pb = (programs.BASE_SHLL_2D if order == 1 else programs.SECOND_ORDER_2D).resized(72, 256)
+def test_2d_every_kernel_variant_gives_the_same_bits(vec, order, tma, oracle, monkeypatch):
+    """LDG kernel (1/2/4 cells per thread) and TMA-fed kernel: different data paths, identical bits."""
+    if (tma == 0 and order == 2 and vec == 4) or (tma == 1 and vec > (2 if order == 1 else 1)):
+        pytest.skip("variant not instantiated")
+    monkeypatch.setenv("SHLL_TMA", str(tma))
+    pb = replace((programs.BASE_SHLL_2D if order == 1 else programs.SECOND_ORDER_2D).resized(72, 256), lx=72 / 256)
     u0 = _random_state(pb, seed=vec)
     got, ref, name = _gpu_vs_oracle(pb, oracle, u0, 11, variant=vec)
-    assert f"vec{vec}" in name
-    assert np.array_equal(bits(got), bits(ref)), name
+    assert f"vec{vec}" in name and (("_tma_" in name) == bool(tma)), name
+    bad = int((bits(got) != bits(ref)).sum())
+    assert bad == 0, f"{name}: {bad} words differ"
+
+
+@pytest.mark.parametrize("stages", [2, 3, 7])
+@pytest.mark.parametrize("rows_per_chunk", [2, 5, 9, 1000])
+def test_2d_tma_ring_geometry_does_not_change_bits(stages, rows_per_chunk, oracle, monkeypatch):
+    """Any ring depth / chunk height (including chunks shorter than a box and a single chunk) gives the same result."""
+    monkeypatch.setenv("SHLL_TMA_STAGES", str(stages))
+    monkeypatch.setenv("SHLL_ROWS_PER_CHUNK", str(rows_per_chunk))
+    for order in (1, 2):
+        pb = replace((programs.BASE_SHLL_2D if order == 1 else programs.SECOND_ORDER_2D).resized(41, 128), lx=41 / 128)
+        u0 = _random_state(pb, seed=stages * 10 + order)
+        got, ref, name = _gpu_vs_oracle(pb, oracle, u0, 6)
+        assert "_tma_" in name
+        assert np.array_equal(bits(got), bits(ref)), name
 
 
 def test_general_dt_ratio_uses_the_exact_double_update(oracle):

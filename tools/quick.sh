@@ -1,6 +1,6 @@
 #!/bin/bash
 # quick GPU iteration: parity tests + dynamic instruction counts + timings for the main kernels
-python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "strict or random or ragged or vector or general or denormal" 2>&1 | tail -4
+python -m pytest tests/test_gpu_parity.py -x -q -m gpu -k "strict or random or ragged or variant or geometry or general or denormal" 2>&1 | tail -12
 for wl in 2d_o1 2d_o2 1d_o1 1d_o2; do
   for mode in strict fast; do
     python bench.py --workload $wl --mode $mode --steps 100 --warmup 5 --no-cpu-baseline --no-e2e 2>&1 | tail -1 | python -c "
