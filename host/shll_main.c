@@ -1,0 +1,222 @@
+/*
+ * shll_main.c -- C host program: the reference's program contract on top of libshll_b200.so.
+ *
+ * One source, four executables (host/Makefile), each a drop-in for one reference program:
+ *
+ *   -DPROGRAM=1  base_shll               base-c/base_shll.c            1D Sod, 1st order, reflective, N=256, t=0.2
+ *   -DPROGRAM=2  base_shll_2d            base-c/base_shll_2d.c         2D implosion, 1st order, reflective, 256^2, t=0.1
+ *   -DPROGRAM=3  2nd_order_base_shll     base-c/2nd_order_base_shll.c  2D four-shock, 2nd order (minmod), outflow, 256^2, t=0.8
+ *   -DPROGRAM=4  2nd_order_base_shll_1d  derived: the x-sweep of program 3 on a 1D Sod tube, t=0.2
+ *
+ * Same shape as the reference's main() (base_shll.c:198-225): Allocate_and_Init_Memory, Compute_U_from_P, the float
+ * clock, `Completed in %d steps`, Save_Results (results.dat), Free_Memory.  The three calls inside the reference's time
+ * loop -- Compute_F_from_P, Update_U_from_F, Compute_P_from_U -- run on the GPU: the loop only replays the float clock
+ * to count NO_STEPS, then Run_Time_Steps() hands all of them to shll_run().
+ *
+ * The reference fixes its sizes with `const` globals and is re-edited per run; here they default to the reference's
+ * values and can be overridden without recompiling:  ./base_shll [N]   ./base_shll_2d [NX [NY]]   env SHLL_STEPS=<k>
+ * (fixed step count, needed for N >= 2^24 where the float clock stalls), SHLL_MODE=fast, SHLL_SAVE=0/1.
+ */
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../include/shll_b200.h"
+
+#ifndef PROGRAM
+#define PROGRAM 1
+#endif
+
+#if PROGRAM == 1
+#define DIMS 1
+#define ORDER 1
+#define BC SHLL_BC_REFLECT
+#define DEFAULT_NX 256
+#define DEFAULT_TOTAL_TIME 0.2
+#define SAVE_BY_DEFAULT 1 /* base_shll.c:221 calls Save_Results() */
+#elif PROGRAM == 2
+#define DIMS 2
+#define ORDER 1
+#define BC SHLL_BC_REFLECT
+#define DEFAULT_NX 256
+#define DEFAULT_TOTAL_TIME 0.1
+#define SAVE_BY_DEFAULT 0 /* commented out in base_shll_2d.c:366 */
+#elif PROGRAM == 3
+#define DIMS 2
+#define ORDER 2
+#define BC SHLL_BC_OUTFLOW
+#define DEFAULT_NX 256
+#define DEFAULT_TOTAL_TIME 0.8
+#define SAVE_BY_DEFAULT 0 /* commented out in 2nd_order_base_shll.c:588 */
+#else
+#define DIMS 1
+#define ORDER 2
+#define BC SHLL_BC_OUTFLOW
+#define DEFAULT_NX 256
+#define DEFAULT_TOTAL_TIME 0.2
+#define SAVE_BY_DEFAULT 1
+#endif
+#define NCOMP (DIMS == 1 ? 3 : 4)
+
+/* Problem constants, same names and values as the reference (base_shll.c:16-26). */
+static int NX = DEFAULT_NX, NY = (DIMS == 2 ? DEFAULT_NX : 1), N;
+static const float R = 1.0;
+static const float GAMMA = 1.4;
+static float CV;
+static const float L = 1.0;
+static const float H = 1.0;
+static float DX, DY;
+static const float CFL = 0.25;
+static float DT, DT_ON_DX, DT_ON_DY;
+static int NO_STEPS = 0;
+static float TOTAL_TIME = DEFAULT_TOTAL_TIME;
+
+static float *p[4], *u[4], *a; /* primitives, conserved variables, sound speed: SoA like p0..p3 / u0..u3 */
+static shll_ctx *ctx;
+
+static void die(const char *what, int rc)
+{
+    const char *msg = ctx ? shll_last_error(ctx) : "";
+    if (!msg || !*msg) msg = shll_last_error(NULL); /* errors raised without a context (shll_create, shll_count_steps) */
+    fprintf(stderr, "%s failed (%d): %s\n", what, rc, msg);
+    exit(1);
+}
+
+void Allocate_and_Init_Memory(void)
+{
+    size_t alignment = 32;
+    for (int k = 0; k < NCOMP; k++) {
+        if (posix_memalign((void **)&p[k], alignment, (size_t)N * sizeof(float)) ||
+            posix_memalign((void **)&u[k], alignment, (size_t)N * sizeof(float))) {
+            fprintf(stderr, "out of memory\n");
+            exit(1);
+        }
+    }
+    if (posix_memalign((void **)&a, alignment, (size_t)N * sizeof(float))) exit(1);
+
+    long cell = 0;
+    for (int i = 0; i < NX; i++) {
+        for (int j = 0; j < NY; j++, cell++) {
+            float rho, vx = 0.0, vy = 0.0, T = 1.0;
+#if PROGRAM == 1 || PROGRAM == 4
+            rho = (i < 0.5 * NX) ? 10.0 : 1.0; /* Sod tube, base_shll.c:55-59 */
+#elif PROGRAM == 2
+            int inside = (i > 0.2 * NX) && (i < 0.8 * NX) && (j > 0.2 * NY) && (j < 0.8 * NY);
+            rho = inside ? 1.0 : 10.0; /* implosion, base_shll_2d.c:96-100 */
+#else
+            /* Euler four-shock problem, 2nd_order_base_shll.c:137-145 (cells exactly on a 3/4 line fall to the last state) */
+            int lo_i = i < 0.75 * NX, hi_i = i > 0.75 * NX, lo_j = j < 0.75 * NY, hi_j = j > 0.75 * NY;
+            if (lo_i && lo_j)      { rho = 0.138;  vx = 1.206; vy = 1.206; T = (0.029 / (rho * R)); }
+            else if (hi_i && lo_j) { rho = 0.5323; vx = 0.0;   vy = 1.206; T = (0.3 / (rho * R)); }
+            else if (lo_i && hi_j) { rho = 0.5323; vx = 1.206; vy = 0.0;   T = (0.3 / (rho * R)); }
+            else                   { rho = 1.5;    vx = 0.0;   vy = 0.0;   T = (1.5 / (rho * R)); }
+#endif
+            p[0][cell] = rho;
+            p[1][cell] = vx;
+            if (DIMS == 2) { p[2][cell] = vy; p[3][cell] = T; } else { p[2][cell] = T; }
+        }
+    }
+}
+
+void Free_Memory(void)
+{
+    for (int k = 0; k < NCOMP; k++) { free(p[k]); free(u[k]); }
+    free(a);
+}
+
+void Compute_U_from_P(void)
+{
+    for (long c = 0; c < N; c++) {
+        u[0][c] = p[0][c];
+        u[1][c] = p[0][c] * p[1][c];
+        if (DIMS == 1) {
+            u[2][c] = p[0][c] * (p[2][c] * CV + 0.5 * p[1][c] * p[1][c]); /* base_shll.c:79 */
+        } else {
+            u[2][c] = p[0][c] * p[2][c];
+            u[3][c] = p[0][c] * (p[3][c] * CV + 0.5 * (p[1][c] * p[1][c] + p[2][c] * p[2][c])); /* base_shll_2d.c:130 */
+        }
+    }
+    /* Estimated CFL = ((R + 1)*DT)/DX  (base_shll.c:82-84; base_shll_2d.c:134-136) */
+    DT = (CFL / (R + 1)) * DX;
+    DT_ON_DX = (CFL / (R + 1));
+    DT_ON_DY = DT / DY;
+}
+
+/* Replaces the body of the reference's time loop: NO_STEPS x {Compute_F_from_P; Update_U_from_F; Compute_P_from_U}. */
+void Run_Time_Steps(void)
+{
+    int rc;
+    if ((rc = shll_upload_u(ctx, (const float *const *)u))) die("shll_upload_u", rc);
+    if ((rc = shll_run(ctx, NO_STEPS))) die("shll_run", rc);
+    if ((rc = shll_download_u(ctx, u))) die("shll_download_u", rc);
+    if ((rc = shll_download_p(ctx, p, a))) die("shll_download_p", rc); /* the last Compute_P_from_U */
+}
+
+void Save_Results(void)
+{
+    FILE *fptr = fopen("results.dat", "w");
+    if (!fptr) { perror("results.dat"); exit(1); }
+    if (DIMS == 2) printf("Saving to file\n");
+    long index = 0;
+    for (int i = 0; i < NX; i++) {
+        for (int j = 0; j < NY; j++, index++) {
+            float cx = (i + 0.5) * DX;
+            if (DIMS == 1) {
+                fprintf(fptr, "%e\t%e\t%e\t%e\n", cx, p[0][index], p[1][index], p[2][index]);
+            } else {
+                float cy = (j + 0.5) * DY;
+                fprintf(fptr, "%e\t%e\t%e\t%e\t%e\t%e\n", cx, cy, p[0][index], p[1][index], p[2][index], p[3][index]);
+            }
+        }
+    }
+    fclose(fptr);
+    if (DIMS == 2) printf("Completed saving data\n");
+}
+
+int main(int argc, char **argv)
+{
+    if (argc > 1) NX = atoi(argv[1]);
+    if (DIMS == 2) NY = (argc > 2) ? atoi(argv[2]) : NX;
+    if (getenv("SHLL_TOTAL_TIME")) TOTAL_TIME = (float)atof(getenv("SHLL_TOTAL_TIME"));
+    N = NX * NY;
+    CV = R / (GAMMA - 1.0);
+    DX = L / NX;
+    DY = (DIMS == 2) ? H / NY : 1.0f;
+
+    float time = 0.0;
+    Allocate_and_Init_Memory();
+    Compute_U_from_P();
+
+    shll_config cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.struct_size = sizeof(cfg);
+    cfg.dims = DIMS; cfg.nx = NX; cfg.ny = NY; cfg.order = ORDER; cfg.bc = BC;
+    cfg.limiter = SHLL_LIM_MINMOD; cfg.alpha = 1.25f;
+    cfg.tform = (PROGRAM == 4) ? SHLL_TFORM_2D : SHLL_TFORM_AUTO;
+    cfg.mode = (getenv("SHLL_MODE") && !strcmp(getenv("SHLL_MODE"), "fast")) ? SHLL_MODE_FAST : SHLL_MODE_STRICT;
+    cfg.dt_on_dx = DT_ON_DX; cfg.dt_on_dy = DT_ON_DY;
+    cfg.device = getenv("SHLL_DEVICE") ? atoi(getenv("SHLL_DEVICE")) : 0;
+    cfg.rank = 0; cfg.nranks = 1;
+    int rc = shll_create(&ctx, &cfg);
+    if (rc) die("shll_create", rc);
+
+    /* Take some timesteps: the float clock decides how many (base_shll.c:208-218) */
+    if (getenv("SHLL_STEPS")) {
+        NO_STEPS = atoi(getenv("SHLL_STEPS"));
+    } else {
+        long n = 0;
+        if ((rc = shll_count_steps(DT, TOTAL_TIME, &n))) die("shll_count_steps", rc);
+        while (time < TOTAL_TIME) { time += DT; NO_STEPS += 1; }
+        if (n != NO_STEPS) { fprintf(stderr, "step count mismatch %ld vs %d\n", n, NO_STEPS); return 1; }
+    }
+    Run_Time_Steps();
+
+    printf("Completed in %d steps\n", NO_STEPS);
+    int save = getenv("SHLL_SAVE") ? atoi(getenv("SHLL_SAVE")) : SAVE_BY_DEFAULT;
+    if (save) Save_Results();
+
+    shll_destroy(ctx);
+    Free_Memory();
+    return 0;
+}
