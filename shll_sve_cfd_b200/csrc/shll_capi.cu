@@ -58,6 +58,14 @@ struct shll_ctx {
     int ntiles, nchunks;
     CUtensorMap tmap[2];   // 2D TMA kernels: one 3D map {ny, nx+4, 4} per ping-pong buffer
     CUtensorMap *tmap_dev; // the same two descriptors in device memory
+    cudaGraphExec_t graph; // single-GPU small grids: GRAPH_STEPS consecutive steps captured once (launch-bound regime)
+    bool graph_tried;
+    int graph_cur;         // ping-pong orientation the graph was captured with
+    // persistent 1D march (persist1d.cuh)
+    float *strips;
+    unsigned *round_done;
+    unsigned persist_rounds;  // value of round_done[] after the last persistent launch
+    int persist_blocks, persist_threads, persist_K;
     int tma_stages;
     size_t tma_smem;
     char variant[128];
@@ -309,6 +317,9 @@ int shll_destroy(shll_ctx *c)
     }
     if (c->scratch) cudaFree(c->scratch);
     if (c->tmap_dev) cudaFree(c->tmap_dev);
+    if (c->graph) cudaGraphExecDestroy(c->graph);
+    if (c->strips) cudaFree(c->strips);
+    if (c->round_done) cudaFree(c->round_done);
     if (c->state) cudaFree(c->state);
     if (c->flags) cudaFree(c->flags);
     if (c->ev0) cudaEventDestroy(c->ev0);
@@ -457,13 +468,57 @@ int launch_one_step(shll_ctx *c)
     return SHLL_OK;
 }
 
+// Persistent 1D march: returns SHLL_E_STATE (without touching the error string) when the grid does not fit the scheme.
+int run_persistent_1d(shll_ctx *c, long nsteps)
+{
+    const shll_config &g = c->cfg;
+    if (!c->persist_blocks) {
+        int dev_sms = 0, coop = 0;
+        CK(c, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g.device));
+        CK(c, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, g.device));
+        if (!coop) return SHLL_E_STATE;
+        int K = env_int("SHLL_PERSIST_K", 8);
+        if (K < 1) K = 1;
+        const int h = K * g.order;
+        int nb = dev_sms;
+        while (nb > 1 && g.nx / nb < 2 * h) nb--;             // every block must own at least its two strips
+        const int seg_max = (g.nx + nb - 1) / nb;
+        const int threads = ((seg_max + 2 * h + 31) / 32) * 32;
+        if (threads > 1024 || g.nx < 2 * h) return SHLL_E_STATE;  // too many cells for one cell per thread: streaming kernel
+        c->persist_blocks = nb; c->persist_threads = threads; c->persist_K = K;
+        CK(c, cudaMalloc(&c->strips, (size_t)2 * nb * 2 * 3 * h * sizeof(float)));
+        CK(c, cudaMalloc(&c->round_done, (size_t)nb * sizeof(unsigned)));
+        CK(c, cudaMemsetAsync(c->round_done, 0, (size_t)nb * sizeof(unsigned), c->stream));
+        c->persist_rounds = 0;
+    }
+    Persist1DParams P;
+    memset(&P, 0, sizeof(P));
+    const int in = c->cur, outb = c->cur ^ 1;
+    for (int k = 0; k < 3; k++) { P.in[k] = c->plane(in, k); P.out[k] = c->plane(outb, k); }
+    P.strips = c->strips; P.round_done = c->round_done; P.err = c->flags + 4;
+    P.round_base = c->persist_rounds;
+    P.n = g.nx; P.nblocks = c->persist_blocks; P.K = c->persist_K; P.hmax = c->persist_K * g.order;
+    P.nsteps = nsteps;
+    P.dtdx = g.dt_on_dx; P.half_dtdx = 0.5f * g.dt_on_dx; P.alpha = g.alpha;
+    P.timeout_ns = (unsigned long long)env_int("SHLL_HALO_TIMEOUT_MS", 5000) * 1000000ull;
+    cudaError_t e = launch_persist1d(c->key, P, c->persist_blocks, c->persist_threads, c->stream);
+    if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "persistent 1D launch failed: %s", cudaGetErrorString(e));
+    const long nrounds = (nsteps + c->persist_K - 1) / c->persist_K;
+    c->persist_rounds += (unsigned)(nrounds - 1);
+    c->cur = outb;
+    c->state_index += (unsigned)nsteps;
+    c->epoch += 1;
+    c->launches += 1;
+    return SHLL_OK;
+}
+
 int check_halo_error(shll_ctx *c)
 {
-    if (!multi(c)) return SHLL_OK;
+    if (!multi(c) && !c->persist_blocks) return SHLL_OK;
     unsigned err = 0;
     CK(c, cudaMemcpyAsync(&err, c->flags + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
-    if (err) return fail(c, SHLL_E_TIMEOUT, "rank %d: a neighbour's halo did not arrive within the timeout", c->cfg.rank);
+    if (err) return fail(c, SHLL_E_TIMEOUT, "rank %d: a neighbour's halo (or a neighbouring block's strip) did not arrive within the timeout", c->cfg.rank);
     return SHLL_OK;
 }
 
@@ -548,6 +603,47 @@ int shll_run(shll_ctx *c, long nsteps)
     CK(c, cudaSetDevice(c->cfg.device));
     int rc = check_connected(c);
     if (rc) return rc;
+    // Launch-bound regime, 1D: one cooperative launch keeps every cell in a register for all nsteps (persist1d.cuh).
+    if (c->cfg.dims == 1 && !multi(c) && nsteps >= 32 && env_int("SHLL_PERSIST", 1) != 0) {
+        rc = run_persistent_1d(c, nsteps);
+        if (rc != SHLL_E_STATE) return rc;  // SHLL_E_STATE here means "not eligible": fall through to the launch-per-step paths
+    }
+    // Launch-bound regime (small grids, many steps): replay a CUDA graph of GRAPH_STEPS captured steps instead of
+    // issuing every launch from the host.  GRAPH_STEPS is even, so the ping-pong buffers end where they started.
+    // Multi-GPU runs are excluded: their per-step halo flags are kernel parameters that change every step.
+    constexpr int GRAPH_STEPS = 128;
+    const bool want_graph = !multi(c) && c->ncells <= (1L << 22) && nsteps >= 2 * GRAPH_STEPS && env_int("SHLL_GRAPH", 1) != 0;
+    if (want_graph && !c->graph && !c->graph_tried) {
+        c->graph_tried = true;
+        cudaGraph_t g = nullptr;
+        const int cur0 = c->cur;
+        c->graph_cur = cur0;
+        const unsigned si0 = c->state_index, ep0 = c->epoch;
+        const long l0 = c->launches;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            int crc = SHLL_OK;
+            for (int s = 0; s < GRAPH_STEPS && crc == SHLL_OK; s++) crc = launch_one_step(c);
+            cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+            if (crc == SHLL_OK && e == cudaSuccess && g) {
+                if (cudaGraphInstantiate(&c->graph, g, 0) != cudaSuccess) c->graph = nullptr;
+            }
+            if (g) cudaGraphDestroy(g);
+        }
+        (void)cudaGetLastError();
+        c->cur = cur0; c->state_index = si0; c->epoch = ep0; c->launches = l0;  // the capture executed nothing
+    }
+    if (want_graph && c->graph) {
+        if (c->cur != c->graph_cur) {  // an odd number of single steps happened before: realign the ping-pong
+            rc = launch_one_step(c);
+            if (rc) return rc;
+            nsteps--;
+        }
+        while (nsteps >= GRAPH_STEPS) {
+            CK(c, cudaGraphLaunch(c->graph, c->stream));
+            c->state_index += GRAPH_STEPS; c->epoch += GRAPH_STEPS; c->launches += GRAPH_STEPS;
+            nsteps -= GRAPH_STEPS;
+        }
+    }
     for (long s = 0; s < nsteps; s++) {
         rc = launch_one_step(c);
         if (rc) return rc;

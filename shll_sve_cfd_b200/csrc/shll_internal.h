@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include "persist1d.cuh"
 #include "step1d.cuh"
 #include "step2d.cuh"
 #include "step2d_tma.cuh"
@@ -22,6 +23,9 @@ cudaError_t launch_step2d_tma_o1(const KernelKey &k, const Step2DTmaParams &p, d
 cudaError_t launch_step2d_tma_o2_strict(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step2d_tma_o2_fast(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s);
+
+// Persistent register-resident 1D march (cooperative launch; grid = nblocks, one block per SM).
+cudaError_t launch_persist1d(const KernelKey &k, const Persist1DParams &p, int nblocks, int threads, cudaStream_t s);
 
 // Compute_P_from_U on the device (for shll_download_p) and the diagnostic CFL reduction.
 cudaError_t launch_prim(int dims, int mode, int tform, const float *const u[4], float *const p[4], float *a, long ncells,

@@ -35,6 +35,39 @@ cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, 
     return cudaErrorInvalidValue;
 }
 
+// ---------------------------------------------------------------------------------------------- persistent 1D march
+template <int ORDER, int BC, int LIM, int MODE, int TFORM>
+static cudaError_t go_persist(const KernelKey &k, const Persist1DParams &p, int nblocks, int threads, cudaStream_t s)
+{
+    void *args[] = {const_cast<Persist1DParams *>(&p)};
+    const size_t smem = (size_t)2 * (threads / 32) * 24 * sizeof(float);
+    const void *fn = (MODE == MODE_STRICT && ORDER == 2 && !k.pow2)
+                         ? (const void *)persist1d_kernel<ORDER, BC, LIM, MODE, TFORM, false>
+                         : (const void *)persist1d_kernel<ORDER, BC, LIM, MODE, TFORM, true>;
+    return cudaLaunchCooperativeKernel(fn, dim3(nblocks), dim3(threads), args, smem, s);
+}
+
+template <int ORDER, int BC, int LIM>
+static cudaError_t persist_by_mode(const KernelKey &k, const Persist1DParams &p, int nblocks, int threads, cudaStream_t s)
+{
+    if (k.mode == MODE_FAST) return go_persist<ORDER, BC, LIM, MODE_FAST, TFORM_2D>(k, p, nblocks, threads, s);
+    if (k.tform == TFORM_1D) return go_persist<ORDER, BC, LIM, MODE_STRICT, TFORM_1D>(k, p, nblocks, threads, s);
+    return go_persist<ORDER, BC, LIM, MODE_STRICT, TFORM_2D>(k, p, nblocks, threads, s);
+}
+
+cudaError_t launch_persist1d(const KernelKey &k, const Persist1DParams &p, int nblocks, int threads, cudaStream_t s)
+{
+    if (k.order == 1) {
+        if (k.bc == BC_REFLECT) return persist_by_mode<1, BC_REFLECT, LIM_MINMOD>(k, p, nblocks, threads, s);
+        return persist_by_mode<1, BC_OUTFLOW, LIM_MINMOD>(k, p, nblocks, threads, s);
+    }
+    if (k.bc == BC_REFLECT && k.lim == LIM_MINMOD) return persist_by_mode<2, BC_REFLECT, LIM_MINMOD>(k, p, nblocks, threads, s);
+    if (k.bc == BC_REFLECT && k.lim == LIM_MC) return persist_by_mode<2, BC_REFLECT, LIM_MC>(k, p, nblocks, threads, s);
+    if (k.bc == BC_OUTFLOW && k.lim == LIM_MINMOD) return persist_by_mode<2, BC_OUTFLOW, LIM_MINMOD>(k, p, nblocks, threads, s);
+    if (k.bc == BC_OUTFLOW && k.lim == LIM_MC) return persist_by_mode<2, BC_OUTFLOW, LIM_MC>(k, p, nblocks, threads, s);
+    return cudaErrorInvalidValue;
+}
+
 // ---------------------------------------------------------------------------------------------- Compute_P_from_U
 struct PlanePtrs {
     const float *u[4];
