@@ -94,14 +94,42 @@ struct RowSlot {
 template <int VEC>
 struct YEdge {
     bool tile_has_wall;  // warp-uniform: this column tile contains j == 0 or j == ny-1
-    bool at_lo[VEC], at_hi[VEC];
+    bool ghost_lo;       // this lane's LAST cell is j = -1 (just below the y = 0 wall)
+    bool ghost_hi;       // this lane's FIRST cell is j = ny (just above the y = ny-1 wall)
+    bool outside[VEC];   // cell is outside the domain (TMA zero-fills those; the LDG kernel clamps the load)
+    bool y_inner[VEC];   // order 2: false for wall cells (j = 0, ny-1) and for cells outside the domain
 };
+
+// y walls.  The reference builds the ghost flux of a wall cell from the cell's own split flux
+// (REFLECT: Bottom = (-,-,+,-) * H-(own), base_shll_2d.c:186-189; OUTFLOW: Bottom = H+(own), 2nd_order_base_shll.c:282-285).
+// Both are reproduced BIT FOR BIT by giving the lane just outside the domain a ghost *state* before the fluxes are
+// evaluated -- the wall cell's state with the y momentum mirrored (REFLECT) or copied (OUTFLOW): every product in
+// H+-(ghost) is then the corresponding product of H-+(own) with exact sign flips (RN is sign-symmetric), e.g.
+// H+_0(ghost) = (-h0)(-Z3) + u0*Z2 = -H-_0(own).  The flux code therefore has no wall selects at all; only the first
+// and last column tile execute this (warp-uniform branch).  tests: every golden fixture + random states, both BCs.
+template <int BC, int VEC>
+__device__ __forceinline__ void plant_y_ghosts(float (&u)[VEC][4], const YEdge<VEC> &Y)
+{
+    const unsigned full = 0xffffffffu;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float from_hi = __shfl_down_sync(full, u[0][k], 1);      // state of cell j+1 (first cell of the next lane)
+        const float from_lo = __shfl_up_sync(full, u[VEC - 1][k], 1);  // state of cell j-1 (last cell of the previous lane)
+        const float sgn = (BC == BC_REFLECT && k == 2) ? -1.0f : 1.0f;
+#pragma unroll
+        for (int v = 0; v < VEC; v++)
+            if (Y.outside[v]) u[v][k] = 1.0f;           // cells further out are never used: keep them a benign gas state
+        if (Y.ghost_lo) u[VEC - 1][k] = sgn * from_hi;  // this lane's last cell is j = -1
+        if (Y.ghost_hi) u[0][k] = sgn * from_lo;        // this lane's first cell is j = ny
+    }
+}
 
 // Fluxes of one row of cells held by the warp + everything the y direction contributes to their update.
 template <int ORDER, int BC, int LIM, int MODE, int VEC>
 __device__ __forceinline__ void row_compute(RowSlot<VEC> &S, const YEdge<VEC> &Y, float alpha)
 {
     const unsigned full = 0xffffffffu;
+    if (Y.tile_has_wall) plant_y_ghosts<BC, VEC>(S.u, Y);  // warp-uniform: first / last column tile only
     float hp[VEC][4], hm[VEC][4];
 #pragma unroll
     for (int v = 0; v < VEC; v++) cell_flux_2d<MODE>(S.u[v], S.fp[v], S.fm[v], hp[v], hm[v]);
@@ -116,48 +144,32 @@ __device__ __forceinline__ void row_compute(RowSlot<VEC> &S, const YEdge<VEC> &Y
             bottom[v] = (v > 0) ? hp[v > 0 ? v - 1 : 0][k] : hp_from_lo;
             top[v] = (v < VEC - 1) ? hm[v < VEC - 1 ? v + 1 : 0][k] : hm_from_hi;
         }
-        float dhp[VEC], dhm[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) S.s1[v][k] = flux_sum<MODE>(hp[v][k], hm[v][k], top[v], bottom[v]);
         if (ORDER == 2) {
             const float hm_from_lo = __shfl_up_sync(full, hm[VEC - 1][k], 1);
             const float hp_from_hi = __shfl_down_sync(full, hp[0][k], 1);
+            float dhp[VEC], dhm[VEC];
 #pragma unroll
-            for (int v = 0; v < VEC; v++) {  // 2nd_order_base_shll.c:336-343 (on the un-patched neighbours)
+            for (int v = 0; v < VEC; v++) {  // 2nd_order_base_shll.c:336-343
                 const float hmL = (v > 0) ? hm[v > 0 ? v - 1 : 0][k] : hm_from_lo;
                 const float hpR = (v < VEC - 1) ? hp[v < VEC - 1 ? v + 1 : 0][k] : hp_from_hi;
                 dhp[v] = limited_slope<LIM>(bottom[v], hp[v][k], hpR, alpha);
                 dhm[v] = limited_slope<LIM>(hmL, hm[v][k], top[v], alpha);
+                // first order in wall cells (:292-300,314-322)
+                dhp[v] = Y.y_inner[v] ? dhp[v] : 0.0f;
+                dhm[v] = Y.y_inner[v] ? dhm[v] : 0.0f;
             }
-        }
-        if (Y.tile_has_wall) {  // warp-uniform: only the first and last column tile
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                if (Y.at_lo[v]) bottom[v] = wall_flux<BC>(hp[v][k], hm[v][k], k, 2);
-                if (Y.at_hi[v]) top[v] = wall_flux<BC>(hm[v][k], hp[v][k], k, 2);
-                if (ORDER == 2) {
-                    if (Y.at_lo[v] || Y.at_hi[v]) dhp[v] = dhm[v] = 0.0f;  // :292-300,314-322
-                }
-            }
-        }
-#pragma unroll
-        for (int v = 0; v < VEC; v++) S.s1[v][k] = flux_sum<MODE>(hp[v][k], hm[v][k], top[v], bottom[v]);
-        if (ORDER == 2) {
             const float dhp_from_lo = __shfl_up_sync(full, dhp[VEC - 1], 1);
             const float dhm_from_hi = __shfl_down_sync(full, dhm[0], 1);
-            float bdf[VEC], tdf[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
-                bdf[v] = (v > 0) ? dhp[v > 0 ? v - 1 : 0] : dhp_from_lo;              // Bottom_df = dhp[j-1]
-                tdf[v] = (v < VEC - 1) ? dhm[v < VEC - 1 ? v + 1 : 0] : dhm_from_hi;  // Top_df = dhm[j+1]
+                // Bottom_df = dhp[j-1], Top_df = dhm[j+1]; both are 0 beyond a wall (:396-399,412-415) -- automatically,
+                // because the ghost lane's y_inner is false as well.
+                const float bdf = (v > 0) ? dhp[v > 0 ? v - 1 : 0] : dhp_from_lo;
+                const float tdf = (v < VEC - 1) ? dhm[v < VEC - 1 ? v + 1 : 0] : dhm_from_hi;
+                S.s2[v][k] = slope_sum(dhp[v], dhm[v], tdf, bdf);
             }
-            if (Y.tile_has_wall) {
-#pragma unroll
-                for (int v = 0; v < VEC; v++) {
-                    if (Y.at_lo[v]) bdf[v] = 0.0f;  // 2nd_order_base_shll.c:396-399
-                    if (Y.at_hi[v]) tdf[v] = 0.0f;  // :412-415
-                }
-            }
-#pragma unroll
-            for (int v = 0; v < VEC; v++) S.s2[v][k] = slope_sum(dhp[v], dhm[v], tdf[v], bdf[v]);
         }
     }
 }
@@ -170,6 +182,7 @@ struct RowCtx {
     int ny, r0, r1;
     int jl, j0;          // clamped load column, own column
     int rmin, rmax;      // rows that exist in memory: [rmin, rmax]
+    int first_real_row, last_real_row;  // rows beyond a physical wall are ghosts: never recomputed, never sloped
     int wall_lo_row;     // 0 if local row 0 is a physical wall, else a row index that never occurs
     int wall_hi_row;     // nx-1 if local row nx-1 is a physical wall, else never
     int peer_lo_end;     // rows [0, peer_lo_end) are also stored into the lower neighbour's halo (0 if none)
@@ -217,22 +230,37 @@ struct RowCtx {
 
 // ---- order 1: finish row i.  A = row i-1 (F+ valid), B = row i (complete), C = row i+1 (fluxes just computed).
 // X supplies the wall rows and the store (RowCtx for the LDG kernel, TmaCtx for the TMA kernel).
+template <int BC, int VEC>
+__device__ __forceinline__ void ghost_below(RowSlot<VEC> &G, const RowSlot<VEC> &B)
+{   // physical wall below row B: the ghost row's F+ is B's own wall flux, its slope is zero
+    // (base_shll_2d.c:152-155; 2nd_order_base_shll.c:216-219,362-365)
+#pragma unroll
+    for (int v = 0; v < VEC; v++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            G.fp[v][k] = wall_flux<BC>(B.fp[v][k], B.fm[v][k], k, 1);
+            G.dfp[v][k] = 0.0f;
+        }
+}
+template <int BC, int VEC>
+__device__ __forceinline__ void ghost_above(RowSlot<VEC> &G, const RowSlot<VEC> &B)
+{   // physical wall above row B (base_shll_2d.c:168-171; 2nd_order_base_shll.c:243-246,378-381)
+#pragma unroll
+    for (int v = 0; v < VEC; v++)
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            G.fm[v][k] = wall_flux<BC>(B.fm[v][k], B.fp[v][k], k, 1);
+            G.dfm[v][k] = 0.0f;
+        }
+}
+
+// ---- order 1: finish row i.  A = row i-1 (F+ valid), B = row i (complete), C = row i+1 (fluxes just computed).
+// At a physical wall the missing neighbour slot already holds the ghost flux (ghost_below / ghost_above are applied
+// where that row would have been computed), so the hot path has no boundary selects.
 template <int BC, int MODE, int VEC, class Ctx>
 __device__ __forceinline__ void finish_o1(const Ctx &X, int i, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C)
 {
     const Step2DParams &P = *X.P;
-    if (i == X.wall_lo_row) {  // base_shll_2d.c:152-155 -- the ghost flux replaces the F+ of the non-existent row -1
-#pragma unroll
-        for (int v = 0; v < VEC; v++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) A.fp[v][k] = wall_flux<BC>(B.fp[v][k], B.fm[v][k], k, 1);
-    }
-    if (i == X.wall_hi_row) {  // :168-171
-#pragma unroll
-        for (int v = 0; v < VEC; v++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) C.fm[v][k] = wall_flux<BC>(B.fm[v][k], B.fp[v][k], k, 1);
-    }
     float uo[VEC][4];
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
@@ -260,7 +288,10 @@ __device__ __forceinline__ void finish_o2(const Ctx &X, int r, RowSlot<VEC> &A, 
             for (int v = 0; v < VEC; v++)
 #pragma unroll
                 for (int k = 0; k < 4; k++) C.dfp[v][k] = C.dfm[v][k] = 0.0f;
-        } else {
+            // the rows beyond the wall do not exist: their slots get the ghost fluxes of the wall row (rarely taken branch)
+            if (rc == X.wall_lo_row) ghost_below<BC, VEC>(B, C);   // B = row -1
+            if (rc == X.wall_hi_row) ghost_above<BC, VEC>(D, C);   // D = row nx
+        } else if (rc >= X.first_real_row && rc <= X.last_real_row) {
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
 #pragma unroll
@@ -273,24 +304,6 @@ __device__ __forceinline__ void finish_o2(const Ctx &X, int r, RowSlot<VEC> &A, 
     }
     const int i = r - 2;
     if (i < X.r0) return;  // still filling the window
-    if (i == X.wall_lo_row) {  // :216-219 ghost flux, :362-365 Left_df = 0
-#pragma unroll
-        for (int v = 0; v < VEC; v++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                A.fp[v][k] = wall_flux<BC>(B.fp[v][k], B.fm[v][k], k, 1);
-                A.dfp[v][k] = 0.0f;
-            }
-    }
-    if (i == X.wall_hi_row) {  // :243-246, :378-381
-#pragma unroll
-        for (int v = 0; v < VEC; v++)
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                C.fm[v][k] = wall_flux<BC>(B.fm[v][k], B.fp[v][k], k, 1);
-                C.dfm[v][k] = 0.0f;
-            }
-    }
     float uo[VEC][4];
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
@@ -313,6 +326,7 @@ __device__ __forceinline__ void step_o1(const RowCtx<VEC> &X, int i, RowSlot<VEC
     if (i >= X.r1) return;
     if (i + 2 <= X.r1 && X.row_exists(i + 2)) X.load_row(i + 2, A.u);
     if (X.row_exists(i + 1)) row_compute<1, BC, LIM, MODE, VEC>(C, X.Y, X.P->alpha);
+    else ghost_above<BC, VEC>(C, B);  // i is the wall row nx-1
     finish_o1<BC, MODE, VEC>(X, i, A, B, C);
 }
 
@@ -348,10 +362,12 @@ __global__ void __launch_bounds__(128) step2d_kernel(const __grid_constant__ Ste
     X.jl = min(max(X.j0, 0), X.ny - VEC);  // clamped load column (lanes outside the domain hold unused values)
     X.owner = (lane >= HL) && (lane < 32 - HL) && (X.j0 < X.ny);
     X.Y.tile_has_wall = (tile == 0) || (tile == P.ntiles - 1);
+    X.Y.ghost_lo = (X.j0 + VEC - 1 == -1);
+    X.Y.ghost_hi = (X.j0 == X.ny);
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
-        X.Y.at_lo[v] = (X.j0 + v == 0);
-        X.Y.at_hi[v] = (X.j0 + v == X.ny - 1);
+        X.Y.y_inner[v] = (X.j0 + v > 0 && X.j0 + v < X.ny - 1);
+        X.Y.outside[v] = (X.j0 + v < 0 || X.j0 + v >= X.ny);
     }
     X.r0 = (int)(((long)chunk * nx) / P.nchunks);
     X.r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
@@ -360,6 +376,8 @@ __global__ void __launch_bounds__(128) step2d_kernel(const __grid_constant__ Ste
     X.rmax = P.hi_wall ? nx - 1 : nx + 1;
     X.wall_lo_row = P.lo_wall ? 0 : never;
     X.wall_hi_row = P.hi_wall ? nx - 1 : never;
+    X.first_real_row = P.lo_wall ? 0 : never;
+    X.last_real_row = P.hi_wall ? nx - 1 : -never;
     X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? ORDER : 0;
     X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - ORDER : 0x7fffffff;
     const bool touch_lo = (X.r0 < ORDER), touch_hi = (X.r1 > nx - ORDER);
@@ -385,6 +403,7 @@ __global__ void __launch_bounds__(128) step2d_kernel(const __grid_constant__ Ste
         X.load_row(X.r0, B.u);
         if (X.row_exists(X.r0 + 1)) X.load_row(X.r0 + 1, C.u);
         row_compute<1, BC, LIM, MODE, VEC>(B, X.Y, P.alpha);
+        if (X.r0 == X.wall_lo_row) ghost_below<BC, VEC>(A, B);
         for (int i = X.r0; i < X.r1; i += 3) {  // roles rotate: no register copies
             step_o1<BC, LIM, MODE, VEC>(X, i, A, B, C);
             step_o1<BC, LIM, MODE, VEC>(X, i + 1, B, C, A);

@@ -6,7 +6,7 @@
 // ONE warp with a private shared-memory ring of STAGES boxes; each box is R rows x 32*VEC columns x 4 planes, fetched by
 // ONE `cp.async.bulk.tensor.3d` (TMA) copy issued by one lane and tracked by an mbarrier.  The warp reads its cells
 // back with conflict-free LDS at constant offsets, so loads cost no address arithmetic, (STAGES-1)*R rows per warp are
-// in flight, and out-of-domain halo lanes are zero-filled by the TMA unit instead of being clamped by hand.
+// in flight, and out-of-domain halo lanes are zero-filled by the TMA unit (plant_y_ghosts then gives them a ghost / benign state).
 // With one warp per block the tile / chunk / row bookkeeping is warp-uniform by construction and runs on the uniform
 // datapath (no convergence barriers around the row predicates).
 //
@@ -70,7 +70,7 @@ struct TmaCtx {
     const Step2DParams *P;
     const Step2DTmaParams *T;
     int ny, r0, r1, j0;
-    int wall_lo_row, wall_hi_row, peer_lo_end, peer_hi_begin;
+    int wall_lo_row, wall_hi_row, first_real_row, last_real_row, peer_lo_end, peer_hi_begin;
     bool owner;
     YEdge<VEC> Y;
     // ring
@@ -93,19 +93,6 @@ struct TmaCtx {
         mbar_expect_tx(bar, STAGE_BYTES);
         tma_load_3d(ring + STAGE_STRIDE * stage, T->tmap_global ? T->tmap_global : &T->tmap, x0, ybase + box * R, 0, bar);
     }
-    // TMA zero-fills cells outside the domain; a zero density would send those (unused) lanes through the IEEE slow
-    // paths of every divide and drag the whole warp: give them a benign gas state instead.  First/last column tile only.
-    __device__ __forceinline__ void sanitize(float (&u)[VEC][4]) const
-    {
-        if (Y.tile_has_wall) {
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                const bool outside = (j0 + v < 0) || (j0 + v >= ny);
-#pragma unroll
-                for (int k = 0; k < 4; k++) u[v][k] = outside ? 1.0f : u[v][k];
-            }
-        }
-    }
     // read row `within` of the box sitting in `stage`
     template <int WITHIN>
     __device__ __forceinline__ void read_row(int stage, float (&u)[VEC][4]) const
@@ -123,7 +110,6 @@ struct TmaCtx {
                              : "r"(a + k * PLANE_BYTES));
             }
         }
-        sanitize(u);
     }
     template <int ORDER>
     __device__ __forceinline__ void store_row(int i, const float (&u)[VEC][4]) const
@@ -174,16 +160,20 @@ __global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ 
     X.j0 = xs + lane * VEC;
     X.owner = (lane >= HL) && (lane < 32 - HL) && (X.j0 < X.ny);
     X.Y.tile_has_wall = (tile == 0) || (tile == P.ntiles - 1);
+    X.Y.ghost_lo = (X.j0 + VEC - 1 == -1);
+    X.Y.ghost_hi = (X.j0 == X.ny);
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
-        X.Y.at_lo[v] = (X.j0 + v == 0);
-        X.Y.at_hi[v] = (X.j0 + v == X.ny - 1);
+        X.Y.y_inner[v] = (X.j0 + v > 0 && X.j0 + v < X.ny - 1);
+        X.Y.outside[v] = (X.j0 + v < 0 || X.j0 + v >= X.ny);
     }
     X.r0 = (int)(((long)chunk * nx) / P.nchunks);
     X.r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
     const int never = -(1 << 30);
     X.wall_lo_row = P.lo_wall ? 0 : never;
     X.wall_hi_row = P.hi_wall ? nx - 1 : never;
+    X.first_real_row = P.lo_wall ? 0 : never;
+    X.last_real_row = P.hi_wall ? nx - 1 : -never;
     X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? ORDER : 0;
     X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - ORDER : 0x7fffffff;
     const int rmax = P.hi_wall ? nx - 1 : nx + 1;  // last row that exists in memory
@@ -235,10 +225,12 @@ __global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ 
         X.template read_row<1>(stage, B.u);
         if (rbeg >= rmin) row_compute<1, BC, LIM, MODE, VEC>(A, X.Y, P.alpha);
         row_compute<1, BC, LIM, MODE, VEC>(B, X.Y, P.alpha);
+        if (X.r0 == X.wall_lo_row) ghost_below<BC, VEC>(A, B);
         for (int i = X.r0; i < X.r1; i += 3) {
             // p = 0: row i+1 is the last row of the current box
             X.template read_row<2>(stage, C.u);
             if (i + 1 <= rmax) row_compute<1, BC, LIM, MODE, VEC>(C, X.Y, P.alpha);
+            else ghost_above<BC, VEC>(C, B);
             finish_o1<BC, MODE, VEC>(X, i, A, B, C);
             next_box();
             if (i + 1 >= X.r1) break;
@@ -246,11 +238,13 @@ __global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ 
             mbar_wait(X.bars + 8u * stage, parity);
             X.template read_row<0>(stage, A.u);
             if (i + 2 <= rmax) row_compute<1, BC, LIM, MODE, VEC>(A, X.Y, P.alpha);
+            else ghost_above<BC, VEC>(A, C);
             finish_o1<BC, MODE, VEC>(X, i + 1, B, C, A);
             if (i + 2 >= X.r1) break;
             // p = 2
             X.template read_row<1>(stage, B.u);
             if (i + 3 <= rmax) row_compute<1, BC, LIM, MODE, VEC>(B, X.Y, P.alpha);
+            else ghost_above<BC, VEC>(B, A);
             finish_o1<BC, MODE, VEC>(X, i + 2, C, A, B);
         }
     } else {
