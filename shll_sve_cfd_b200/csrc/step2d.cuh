@@ -134,43 +134,58 @@ __device__ __forceinline__ void row_compute(RowSlot<VEC> &S, const YEdge<VEC> &Y
 #pragma unroll
     for (int v = 0; v < VEC; v++) cell_flux_2d<MODE>(S.u[v], S.fp[v], S.fm[v], hp[v], hm[v]);
 
+    // neighbours across the lane boundary: H+ of cell j-1 ("bottom"), H- of cell j+1 ("top")
+    float bottom[VEC][4], top[VEC][4];
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-        float bottom[VEC], top[VEC];  // H+ of cell j-1, H- of cell j+1
         const float hp_from_lo = __shfl_up_sync(full, hp[VEC - 1][k], 1);
         const float hm_from_hi = __shfl_down_sync(full, hm[0][k], 1);
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
-            bottom[v] = (v > 0) ? hp[v > 0 ? v - 1 : 0][k] : hp_from_lo;
-            top[v] = (v < VEC - 1) ? hm[v < VEC - 1 ? v + 1 : 0][k] : hm_from_hi;
+            bottom[v][k] = (v > 0) ? hp[v > 0 ? v - 1 : 0][k] : hp_from_lo;
+            top[v][k] = (v < VEC - 1) ? hm[v < VEC - 1 ? v + 1 : 0][k] : hm_from_hi;
         }
+    }
 #pragma unroll
-        for (int v = 0; v < VEC; v++) S.s1[v][k] = flux_sum<MODE>(hp[v][k], hm[v][k], top[v], bottom[v]);
-        if (ORDER == 2) {
+    for (int v = 0; v < VEC; v++) flux_sum4(hp[v], hm[v], top[v], bottom[v], S.s1[v]);
+    if (ORDER == 2) {
+        float hmL[VEC][4], hpR[VEC][4];  // H- of j-1, H+ of j+1
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
             const float hm_from_lo = __shfl_up_sync(full, hm[VEC - 1][k], 1);
             const float hp_from_hi = __shfl_down_sync(full, hp[0][k], 1);
-            float dhp[VEC], dhm[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; v++) {  // 2nd_order_base_shll.c:336-343
-                const float hmL = (v > 0) ? hm[v > 0 ? v - 1 : 0][k] : hm_from_lo;
-                const float hpR = (v < VEC - 1) ? hp[v < VEC - 1 ? v + 1 : 0][k] : hp_from_hi;
-                dhp[v] = limited_slope<LIM>(bottom[v], hp[v][k], hpR, alpha);
-                dhm[v] = limited_slope<LIM>(hmL, hm[v][k], top[v], alpha);
-                // first order in wall cells (:292-300,314-322)
-                dhp[v] = Y.y_inner[v] ? dhp[v] : 0.0f;
-                dhm[v] = Y.y_inner[v] ? dhm[v] : 0.0f;
-            }
-            const float dhp_from_lo = __shfl_up_sync(full, dhp[VEC - 1], 1);
-            const float dhm_from_hi = __shfl_down_sync(full, dhm[0], 1);
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
-                // Bottom_df = dhp[j-1], Top_df = dhm[j+1]; both are 0 beyond a wall (:396-399,412-415) -- automatically,
-                // because the ghost lane's y_inner is false as well.
-                const float bdf = (v > 0) ? dhp[v > 0 ? v - 1 : 0] : dhp_from_lo;
-                const float tdf = (v < VEC - 1) ? dhm[v < VEC - 1 ? v + 1 : 0] : dhm_from_hi;
-                S.s2[v][k] = slope_sum(dhp[v], dhm[v], tdf, bdf);
+                hmL[v][k] = (v > 0) ? hm[v > 0 ? v - 1 : 0][k] : hm_from_lo;
+                hpR[v][k] = (v < VEC - 1) ? hp[v < VEC - 1 ? v + 1 : 0][k] : hp_from_hi;
             }
         }
+        float dhp[VEC][4], dhm[VEC][4];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) {  // 2nd_order_base_shll.c:336-343; first order in wall cells (:292-300,314-322)
+            limited_slope4<LIM>(bottom[v], hp[v], hpR[v], alpha, dhp[v]);
+            limited_slope4<LIM>(hmL[v], hm[v], top[v], alpha, dhm[v]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                dhp[v][k] = Y.y_inner[v] ? dhp[v][k] : 0.0f;
+                dhm[v][k] = Y.y_inner[v] ? dhm[v][k] : 0.0f;
+            }
+        }
+        // Bottom_df = dhp[j-1], Top_df = dhm[j+1]; both are 0 beyond a wall (:396-399,412-415) -- automatically,
+        // because the ghost lane's y_inner is false as well.
+        float bdf[VEC][4], tdf[VEC][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float dhp_from_lo = __shfl_up_sync(full, dhp[VEC - 1][k], 1);
+            const float dhm_from_hi = __shfl_down_sync(full, dhm[0][k], 1);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) {
+                bdf[v][k] = (v > 0) ? dhp[v > 0 ? v - 1 : 0][k] : dhp_from_lo;
+                tdf[v][k] = (v < VEC - 1) ? dhm[v < VEC - 1 ? v + 1 : 0][k] : dhm_from_hi;
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < VEC; v++) slope_sum4(dhp[v], dhm[v], tdf[v], bdf[v], S.s2[v]);
     }
 }
 
@@ -264,12 +279,10 @@ __device__ __forceinline__ void finish_o1(const Ctx &X, int i, RowSlot<VEC> &A, 
     float uo[VEC][4];
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float s = flux_sum<MODE>(B.fp[v][k], B.fm[v][k], C.fm[v][k], A.fp[v][k]);
-            float t = apply_first<MODE>(B.u[v][k], P.dtdx, s);    // base_shll_2d.c:227-230
-            uo[v][k] = apply_first<MODE>(t, P.dtdy, B.s1[v][k]);  // base_shll_2d.c:232-235
-        }
+        float s[4], t[4];
+        flux_sum4(B.fp[v], B.fm[v], C.fm[v], A.fp[v], s);
+        apply_first4<MODE>(B.u[v], P.dtdx, s, t);         // base_shll_2d.c:227-230
+        apply_first4<MODE>(t, P.dtdy, B.s1[v], uo[v]);    // base_shll_2d.c:232-235
     }
     X.template store_row<1>(i, uo);
 }
@@ -294,11 +307,8 @@ __device__ __forceinline__ void finish_o2(const Ctx &X, int r, RowSlot<VEC> &A, 
         } else if (rc >= X.first_real_row && rc <= X.last_real_row) {
 #pragma unroll
             for (int v = 0; v < VEC; v++) {
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    C.dfp[v][k] = limited_slope<LIM>(B.fp[v][k], C.fp[v][k], D.fp[v][k], P.alpha);
-                    C.dfm[v][k] = limited_slope<LIM>(B.fm[v][k], C.fm[v][k], D.fm[v][k], P.alpha);
-                }
+                limited_slope4<LIM>(B.fp[v], C.fp[v], D.fp[v], P.alpha, C.dfp[v]);
+                limited_slope4<LIM>(B.fm[v], C.fm[v], D.fm[v], P.alpha, C.dfm[v]);
             }
         }
     }
@@ -307,14 +317,13 @@ __device__ __forceinline__ void finish_o2(const Ctx &X, int r, RowSlot<VEC> &A, 
     float uo[VEC][4];
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            float s = flux_sum<MODE>(B.fp[v][k], B.fm[v][k], C.fm[v][k], A.fp[v][k]);
-            float t = apply_first<MODE>(B.u[v][k], P.dtdx, s);  // :438
-            t = apply_second<MODE, POW2>(t, P.half_dtdx, slope_sum(B.dfp[v][k], B.dfm[v][k], C.dfm[v][k], A.dfp[v][k]));  // :443
-            t = apply_first<MODE>(t, P.dtdy, B.s1[v][k]);                     // :449
-            uo[v][k] = apply_second<MODE, POW2>(t, P.half_dtdy, B.s2[v][k]);  // :454
-        }
+        float s[4], d[4], t1[4], t2[4], t3[4];
+        flux_sum4(B.fp[v], B.fm[v], C.fm[v], A.fp[v], s);
+        apply_first4<MODE>(B.u[v], P.dtdx, s, t1);                       // 2nd_order_base_shll.c:438
+        slope_sum4(B.dfp[v], B.dfm[v], C.dfm[v], A.dfp[v], d);
+        apply_second4<MODE, POW2>(t1, P.half_dtdx, d, t2);               // :443
+        apply_first4<MODE>(t2, P.dtdy, B.s1[v], t3);                     // :449
+        apply_second4<MODE, POW2>(t3, P.half_dtdy, B.s2[v], uo[v]);      // :454
     }
     X.template store_row<2>(i, uo);
 }
