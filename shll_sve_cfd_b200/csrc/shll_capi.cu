@@ -121,15 +121,16 @@ void plan_2d(shll_ctx *c)
     // TMA-fed kernel (step2d_tma.cuh) whenever the row stride is a multiple of 16 bytes; SHLL_TMA=0 forces the LDG kernel.
     c->key.tma = (g.ny % 4 == 0) && (g.ny >= 32) && env_int("SHLL_TMA", 1) != 0;
     if (c->key.tma) {
-        const int maxvec = (g.order == 1) ? 2 : 1;  // instantiated TMA widths
-        if (g.variant <= 0 && env_int("SHLL_VEC", 0) <= 0) vec = 1;
-        if (vec > maxvec) vec = maxvec;
+        // defaults from the B200 sweep (profiles/r01_sweep_2d.log): order 1 FAST 2 cells per lane, everything else 1
+        if (g.variant <= 0 && env_int("SHLL_VEC", 0) <= 0) vec = (g.order == 1 && g.mode == SHLL_MODE_FAST) ? 2 : 1;
+        if (vec > 2) vec = 2;  // instantiated TMA widths
+        while (vec > 1 && (g.ny % (4 * vec) != 0 || g.ny < 32 * vec)) vec >>= 1;
     }
     c->key.vec = vec;
     const int hl = (g.order + vec - 1) / vec;
     const int useful = (32 - 2 * hl) * vec;
     c->ntiles = (g.ny + useful - 1) / useful;
-    int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? 48 : 64);
+    int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? (g.order == 1 ? 24 : 64) : 64);
     if (rpc < 2) rpc = 2;
     int nchunks = (g.nx + rpc - 1) / rpc;
     if (nchunks < 1) nchunks = 1;
@@ -166,7 +167,7 @@ int make_tensor_maps(shll_ctx *c)
         if (cudaMalloc(&c->tmap_dev, 2 * sizeof(CUtensorMap)) != cudaSuccess) return -2;
         if (cudaMemcpy(c->tmap_dev, c->tmap, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
     }
-    c->tma_stages = env_int("SHLL_TMA_STAGES", 4);
+    c->tma_stages = env_int("SHLL_TMA_STAGES", c->key.vec == 2 ? 3 : 4);
     if (c->tma_stages < 2) c->tma_stages = 2;
     if (c->tma_stages > 16) c->tma_stages = 16;
     const size_t stage_stride = ((size_t)4 * R * (32 * c->key.vec + 4) * 4 + 127) & ~(size_t)127;

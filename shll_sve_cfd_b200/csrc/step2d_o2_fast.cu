@@ -35,11 +35,17 @@ cudaError_t launch_step2d_o2_fast(const KernelKey &k, const Step2DParams &p, dim
 
 cudaError_t launch_step2d_tma_o2_fast(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
 {
-    if (k.vec != 1) return cudaErrorInvalidValue;
-    if (k.bc == BC_REFLECT && k.lim == LIM_MINMOD) return go_tma<BC_REFLECT, LIM_MINMOD, 1>(p, grid, smem, s);
-    if (k.bc == BC_REFLECT && k.lim == LIM_MC) return go_tma<BC_REFLECT, LIM_MC, 1>(p, grid, smem, s);
-    if (k.bc == BC_OUTFLOW && k.lim == LIM_MINMOD) return go_tma<BC_OUTFLOW, LIM_MINMOD, 1>(p, grid, smem, s);
-    if (k.bc == BC_OUTFLOW && k.lim == LIM_MC) return go_tma<BC_OUTFLOW, LIM_MC, 1>(p, grid, smem, s);
+    if (k.vec == 1) {
+        if (k.bc == BC_REFLECT && k.lim == LIM_MINMOD) return go_tma<BC_REFLECT, LIM_MINMOD, 1>(p, grid, smem, s);
+        if (k.bc == BC_REFLECT && k.lim == LIM_MC) return go_tma<BC_REFLECT, LIM_MC, 1>(p, grid, smem, s);
+        if (k.bc == BC_OUTFLOW && k.lim == LIM_MINMOD) return go_tma<BC_OUTFLOW, LIM_MINMOD, 1>(p, grid, smem, s);
+        if (k.bc == BC_OUTFLOW && k.lim == LIM_MC) return go_tma<BC_OUTFLOW, LIM_MC, 1>(p, grid, smem, s);
+    } else if (k.vec == 2) {
+        if (k.bc == BC_REFLECT && k.lim == LIM_MINMOD) return go_tma<BC_REFLECT, LIM_MINMOD, 2>(p, grid, smem, s);
+        if (k.bc == BC_REFLECT && k.lim == LIM_MC) return go_tma<BC_REFLECT, LIM_MC, 2>(p, grid, smem, s);
+        if (k.bc == BC_OUTFLOW && k.lim == LIM_MINMOD) return go_tma<BC_OUTFLOW, LIM_MINMOD, 2>(p, grid, smem, s);
+        if (k.bc == BC_OUTFLOW && k.lim == LIM_MC) return go_tma<BC_OUTFLOW, LIM_MC, 2>(p, grid, smem, s);
+    }
     return cudaErrorInvalidValue;
 }
 

@@ -32,9 +32,9 @@ static cudaError_t by_vec(const KernelKey &k, const Step2DParams &p, dim3 grid, 
 template <int BC, int LIM>
 static cudaError_t by_vec_tma(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
 {
-    if (k.vec != 1) return cudaErrorInvalidValue;
-    if (k.pow2) return go_tma<BC, LIM, 1, true>(p, grid, smem, s);
-    return go_tma<BC, LIM, 1, false>(p, grid, smem, s);
+    if (k.vec == 1) return k.pow2 ? go_tma<BC, LIM, 1, true>(p, grid, smem, s) : go_tma<BC, LIM, 1, false>(p, grid, smem, s);
+    if (k.vec == 2) return k.pow2 ? go_tma<BC, LIM, 2, true>(p, grid, smem, s) : go_tma<BC, LIM, 2, false>(p, grid, smem, s);
+    return cudaErrorInvalidValue;
 }
 
 cudaError_t launch_step2d_o2_strict(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s)

@@ -140,7 +140,7 @@ def test_2d_ragged_sizes(shape, order, oracle):
 @pytest.mark.parametrize("order", [1, 2])
 def test_2d_every_kernel_variant_gives_the_same_bits(vec, order, tma, oracle, monkeypatch):
     """LDG kernel (1/2/4 cells per thread) and TMA-fed kernel: different data paths, identical bits."""
-    if (tma == 0 and order == 2 and vec == 4) or (tma == 1 and vec > (2 if order == 1 else 1)):
+    if (tma == 0 and order == 2 and vec == 4) or (tma == 1 and vec > 2):
         pytest.skip("variant not instantiated")
     monkeypatch.setenv("SHLL_TMA", str(tma))
     pb = replace((programs.BASE_SHLL_2D if order == 1 else programs.SECOND_ORDER_2D).resized(72, 256), lx=72 / 256)
