@@ -62,9 +62,10 @@ __device__ __forceinline__ void halo_wait(const HaloSync &S, const unsigned *fla
     if ((threadIdx.x & 31) == 0) {
         if ((int)(ld_acquire_sys(flag) - S.want) < 0) {
             const unsigned long long t0 = globaltimer_ns();
+            unsigned polls = 0;
             while ((int)(ld_acquire_sys(flag) - S.want) < 0) {
-                __nanosleep(64);
-                if (globaltimer_ns() - t0 > S.timeout_ns) {
+                __nanosleep(32);
+                if ((++polls & 255u) == 0 && globaltimer_ns() - t0 > S.timeout_ns) {
                     atomicExch(S.err, 1u);
                     break;
                 }

@@ -77,16 +77,21 @@ __global__ void __launch_bounds__(1024, 1) persist1d_kernel(const Persist1DParam
         if (r > 0) {
             // ---- halo refresh from the neighbours' strips of round r-1
             const unsigned want = P.round_base + (unsigned)r;
-            if (t == 0) {
-                const unsigned long long t0 = globaltimer_ns();
-                bool ok = true;
-                while (ok && have_lo && (int)(ld_acquire_gpu(P.round_done + b - 1) - want) < 0) {
-                    if (globaltimer_ns() - t0 > P.timeout_ns || *(volatile unsigned *)P.err) { atomicExch(P.err, 1u); ok = false; }
-                }
-                while (ok && have_hi && (int)(ld_acquire_gpu(P.round_done + b + 1) - want) < 0) {
-                    if (globaltimer_ns() - t0 > P.timeout_ns || *(volatile unsigned *)P.err) { atomicExch(P.err, 1u); ok = false; }
+            if (t < 2) {  // thread 0 watches the lower neighbour, thread 1 the upper one; the clock is read every 1024 polls only
+                const bool have = (t == 0) ? have_lo : have_hi;
+                const unsigned *flag = P.round_done + (t == 0 ? b - 1 : b + 1);
+                if (have && (int)(ld_acquire_gpu(flag) - want) < 0) {
+                    const unsigned long long t0 = globaltimer_ns();
+                    unsigned polls = 0;
+                    while ((int)(ld_acquire_gpu(flag) - want) < 0) {
+                        if ((++polls & 1023u) == 0 && (globaltimer_ns() - t0 > P.timeout_ns || *(volatile unsigned *)P.err)) {
+                            atomicExch(P.err, 1u);
+                            break;
+                        }
+                    }
                 }
             }
+            __syncthreads();
             if (t == 0) sh_abort = *(volatile unsigned *)P.err;
             __syncthreads();
             if (sh_abort) return;  // a neighbour never showed up: the whole block bails out (the host reports the error)

@@ -478,7 +478,7 @@ int run_persistent_1d(shll_ctx *c, long nsteps)
         CK(c, cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, g.device));
         CK(c, cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, g.device));
         if (!coop) return SHLL_E_STATE;
-        int K = env_int("SHLL_PERSIST_K", 8);
+        int K = env_int("SHLL_PERSIST_K", 16);  // steps per round: B200 sweep, 1.37 us/step at 16 vs 1.57 at 8 (FAST)
         if (K < 1) K = 1;
         const int h = K * g.order;
         int nb = dev_sms;
