@@ -27,25 +27,24 @@ struct Step1DParams {
     HaloSync sync;  // multi-GPU only
 };
 
-template <int ORDER, int BC, int LIM, int MODE, int TFORM, bool POW2>
-__global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
+// One warp tile.  EDGE = false is the interior fast path: no wall selects, no ragged stores, no halo exchange -- the
+// warp-uniform dispatch in step1d_kernel sends only the first tile and the tiles touching the upper end through
+// EDGE = true, so >99.9 % of the warps of a large tube never execute a boundary instruction.
+template <int ORDER, int BC, int LIM, int MODE, int TFORM, bool POW2, bool EDGE>
+__device__ __forceinline__ void step1d_tile(const Step1DParams &P, int tile, int lane)
 {
     constexpr int VEC = 4;
     constexpr int USEFUL = 30 * VEC;
     const unsigned full = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tile >= P.ntiles) return;
     const int n = P.n;
     const int j0 = tile * USEFUL + (lane - 1) * VEC;  // >= -4: inside the padding
     // last float4 that is still inside the allocation [-PAD1D, roundup4(n) + PAD1D)
-    const int jmax = ((n + 3) & ~3);
-    const int jl = min(j0, jmax);
+    const int jl = EDGE ? min(j0, ((n + 3) & ~3)) : j0;
     const bool lo_wall = P.lo_wall != 0, hi_wall = P.hi_wall != 0;
     // warps owning one of the first / last ORDER cells exchange halos with the neighbour GPUs
     const int own_lo = tile * USEFUL, own_hi = min(own_lo + USEFUL, n);  // owned cells [own_lo, own_hi)
-    const bool touch_lo = (own_lo < ORDER), touch_hi = (own_hi > n - ORDER) && (own_lo < n);
-    if (P.sync.enabled) {
+    const bool touch_lo = EDGE && (own_lo < ORDER), touch_hi = EDGE && (own_hi > n - ORDER) && (own_lo < n);
+    if (EDGE && P.sync.enabled) {
         if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
         if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
     }
@@ -62,8 +61,8 @@ __global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
     bool at_lo[VEC], at_hi[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; v++) {
-        at_lo[v] = lo_wall && (j0 + v == 0);
-        at_hi[v] = hi_wall && (j0 + v == n - 1);
+        at_lo[v] = EDGE && lo_wall && (j0 + v == 0);
+        at_hi[v] = EDGE && hi_wall && (j0 + v == n - 1);
     }
 
     float uo[VEC][3];
@@ -81,13 +80,15 @@ __global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
 #pragma unroll
         for (int v = 0; v < VEC; v++) {
             // reflective ends: (-,+,-) on (rho, rho*u, E), base_shll.c:95-97,108-110; outflow: own flux
-            float left, right;
-            if (BC == BC_REFLECT) {
-                left = at_lo[v] ? ((k == 1) ? fm[v][k] : -fm[v][k]) : fpL[v];
-                right = at_hi[v] ? ((k == 1) ? fp[v][k] : -fp[v][k]) : fmR[v];
-            } else {
-                left = at_lo[v] ? fp[v][k] : fpL[v];
-                right = at_hi[v] ? fm[v][k] : fmR[v];
+            float left = fpL[v], right = fmR[v];
+            if (EDGE) {
+                if (BC == BC_REFLECT) {
+                    left = at_lo[v] ? ((k == 1) ? fm[v][k] : -fm[v][k]) : fpL[v];
+                    right = at_hi[v] ? ((k == 1) ? fp[v][k] : -fp[v][k]) : fmR[v];
+                } else {
+                    left = at_lo[v] ? fp[v][k] : fpL[v];
+                    right = at_hi[v] ? fm[v][k] : fmR[v];
+                }
             }
             t1[v] = apply_first<MODE>(u[v][k], P.dtdx, flux_sum<MODE>(fp[v][k], fm[v][k], right, left));  // base_shll.c:124
         }
@@ -99,9 +100,13 @@ __global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
             for (int v = 0; v < VEC; v++) {
                 float fmL = (v > 0) ? fm[v > 0 ? v - 1 : 0][k] : fm_from_lo;
                 float fpR = (v < VEC - 1) ? fp[v < VEC - 1 ? v + 1 : 0][k] : fp_from_hi;
-                bool edge = at_lo[v] || at_hi[v];
-                dfp[v] = edge ? 0.0f : limited_slope<LIM>(fpL[v], fp[v][k], fpR, P.alpha);
-                dfm[v] = edge ? 0.0f : limited_slope<LIM>(fmL, fm[v][k], fmR[v], P.alpha);
+                const bool edge = at_lo[v] || at_hi[v];
+                dfp[v] = limited_slope<LIM>(fpL[v], fp[v][k], fpR, P.alpha);
+                dfm[v] = limited_slope<LIM>(fmL, fm[v][k], fmR[v], P.alpha);
+                if (EDGE) {
+                    dfp[v] = edge ? 0.0f : dfp[v];
+                    dfm[v] = edge ? 0.0f : dfm[v];
+                }
             }
             float dfp_from_lo = __shfl_up_sync(full, dfp[VEC - 1], 1);
             float dfm_from_hi = __shfl_down_sync(full, dfm[0], 1);
@@ -109,8 +114,10 @@ __global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
             for (int v = 0; v < VEC; v++) {
                 float ldf = (v > 0) ? dfp[v > 0 ? v - 1 : 0] : dfp_from_lo;
                 float rdf = (v < VEC - 1) ? dfm[v < VEC - 1 ? v + 1 : 0] : dfm_from_hi;
-                ldf = at_lo[v] ? 0.0f : ldf;
-                rdf = at_hi[v] ? 0.0f : rdf;
+                if (EDGE) {
+                    ldf = at_lo[v] ? 0.0f : ldf;
+                    rdf = at_hi[v] ? 0.0f : rdf;
+                }
                 t1[v] = apply_second<MODE, POW2>(t1[v], P.half_dtdx, slope_sum(dfp[v], dfm[v], rdf, ldf));
             }
         }
@@ -118,6 +125,14 @@ __global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
         for (int v = 0; v < VEC; v++) uo[v][k] = t1[v];
     }
 
+    if (!EDGE) {  // interior tile: every owner lane stores three full float4
+        if (lane != 0 && lane != 31) {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                *reinterpret_cast<float4 *>(P.out[k] + j0) = make_float4(uo[0][k], uo[1][k], uo[2][k], uo[3][k]);
+        }
+        return;
+    }
     const bool owner = !(lane == 0 || lane == 31 || j0 >= n);
 #pragma unroll
     for (int k = 0; k < 3; k++) {
@@ -145,6 +160,18 @@ __global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
         if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);
         if (touch_hi) halo_arrive(P.sync, P.sync.cnt_hi, P.sync.edge_warps_hi, P.sync.sig_hi);
     }
+}
+
+template <int ORDER, int BC, int LIM, int MODE, int TFORM, bool POW2>
+__global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
+{
+    const int lane = threadIdx.x & 31;
+    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tile >= P.ntiles) return;
+    // interior tile: all 128 loaded cells and their +-ORDER neighbours are real owned cells of this slab
+    const bool interior = (tile > 0) && ((long)tile * 120 + 124 + ORDER <= (long)P.n - ORDER);
+    if (interior) step1d_tile<ORDER, BC, LIM, MODE, TFORM, POW2, false>(P, tile, lane);
+    else step1d_tile<ORDER, BC, LIM, MODE, TFORM, POW2, true>(P, tile, lane);
 }
 
 }  // namespace shll
