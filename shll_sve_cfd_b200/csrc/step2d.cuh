@@ -124,10 +124,90 @@ __device__ __forceinline__ void plant_y_ghosts(float (&u)[VEC][4], const YEdge<V
     }
 }
 
+// ---- FAST mode, 2 cells per lane: the lane's two cells as the halves of packed FP32x2 operations (shll_math.cuh,
+// "FAST mode on PAIRS OF CELLS").  Same storage (RowSlot<2>), same op order as the scalar code below, half the FP32 issue
+// slots; only the y neighbours need re-pairing (one half comes from the other cell of the lane, one from a shuffle).
+#define SHLL_PK(arr, k) v2mk((arr)[0][k], (arr)[1][k])
+#define SHLL_UNPK(arr, k, val) do { const v2 t_ = (val); (arr)[0][k] = t_.x; (arr)[1][k] = t_.y; } while (0)
+
+template <int ORDER, int BC, int LIM>
+__device__ __forceinline__ void row_compute_fast_x2(RowSlot<2> &S, const YEdge<2> &Y, float alpha)
+{
+    const unsigned full = 0xffffffffu;
+    if (Y.tile_has_wall) plant_y_ghosts<BC, 2>(S.u, Y);
+    const v2 u[4] = {SHLL_PK(S.u, 0), SHLL_PK(S.u, 1), SHLL_PK(S.u, 2), SHLL_PK(S.u, 3)};
+    v2 fp[4], fm[4], hp[4], hm[4];
+    cell_flux_2d_fast_x2(u, fp, fm, hp, hm);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        SHLL_UNPK(S.fp, k, fp[k]);
+        SHLL_UNPK(S.fm, k, fm[k]);
+        const v2 bottom = v2mk(__shfl_up_sync(full, hp[k].y, 1), hp[k].x);  // H+ of cells j-1
+        const v2 top = v2mk(hm[k].y, __shfl_down_sync(full, hm[k].x, 1));   // H- of cells j+1
+        SHLL_UNPK(S.s1, k, v2sub(v2add(v2sub(hp[k], hm[k]), top), bottom));
+        if (ORDER == 2) {
+            const v2 hmL = v2mk(__shfl_up_sync(full, hm[k].y, 1), hm[k].x);
+            const v2 hpR = v2mk(hp[k].y, __shfl_down_sync(full, hp[k].x, 1));
+            v2 dhp = limited_slope_x2<LIM>(bottom, hp[k], hpR, alpha);
+            v2 dhm = limited_slope_x2<LIM>(hmL, hm[k], top, alpha);
+            dhp.x = Y.y_inner[0] ? dhp.x : 0.0f; dhp.y = Y.y_inner[1] ? dhp.y : 0.0f;
+            dhm.x = Y.y_inner[0] ? dhm.x : 0.0f; dhm.y = Y.y_inner[1] ? dhm.y : 0.0f;
+            const v2 bdf = v2mk(__shfl_up_sync(full, dhp.y, 1), dhp.x);
+            const v2 tdf = v2mk(dhm.y, __shfl_down_sync(full, dhm.x, 1));
+            SHLL_UNPK(S.s2, k, v2sub(v2sub(v2add(dhp, dhm), tdf), bdf));
+        }
+    }
+}
+
+template <class Ctx>
+__device__ __forceinline__ void finish_o1_fast_x2(Ctx &X, int i, RowSlot<2> &A, RowSlot<2> &B, RowSlot<2> &C)
+{
+    const Step2DParams &P = *X.P;
+    float uo[2][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const v2 s = v2sub(v2add(v2sub(SHLL_PK(B.fp, k), SHLL_PK(B.fm, k)), SHLL_PK(C.fm, k)), SHLL_PK(A.fp, k));
+        const v2 t = v2fma(v2bc(-P.dtdx), s, SHLL_PK(B.u, k));
+        SHLL_UNPK(uo, k, v2fma(v2bc(-P.dtdy), SHLL_PK(B.s1, k), t));
+    }
+    X.template store_row<1>(i, uo);
+}
+
+template <int LIM>
+__device__ __forceinline__ void slopes_x_fast_x2(const RowSlot<2> &B, RowSlot<2> &C, const RowSlot<2> &D, float alpha)
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        SHLL_UNPK(C.dfp, k, limited_slope_x2<LIM>(SHLL_PK(B.fp, k), SHLL_PK(C.fp, k), SHLL_PK(D.fp, k), alpha));
+        SHLL_UNPK(C.dfm, k, limited_slope_x2<LIM>(SHLL_PK(B.fm, k), SHLL_PK(C.fm, k), SHLL_PK(D.fm, k), alpha));
+    }
+}
+
+template <class Ctx>
+__device__ __forceinline__ void update_o2_fast_x2(Ctx &X, int i, RowSlot<2> &A, RowSlot<2> &B, RowSlot<2> &C)
+{
+    const Step2DParams &P = *X.P;
+    float uo[2][4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const v2 s = v2sub(v2add(v2sub(SHLL_PK(B.fp, k), SHLL_PK(B.fm, k)), SHLL_PK(C.fm, k)), SHLL_PK(A.fp, k));
+        v2 t = v2fma(v2bc(-P.dtdx), s, SHLL_PK(B.u, k));
+        const v2 d = v2sub(v2sub(v2add(SHLL_PK(B.dfp, k), SHLL_PK(B.dfm, k)), SHLL_PK(C.dfm, k)), SHLL_PK(A.dfp, k));
+        t = v2fma(v2bc(-P.half_dtdx), d, t);
+        t = v2fma(v2bc(-P.dtdy), SHLL_PK(B.s1, k), t);
+        SHLL_UNPK(uo, k, v2fma(v2bc(-P.half_dtdy), SHLL_PK(B.s2, k), t));
+    }
+    X.template store_row<2>(i, uo);
+}
+
 // Fluxes of one row of cells held by the warp + everything the y direction contributes to their update.
 template <int ORDER, int BC, int LIM, int MODE, int VEC>
 __device__ __forceinline__ void row_compute(RowSlot<VEC> &S, const YEdge<VEC> &Y, float alpha)
 {
+    if constexpr (VEC == 2 && MODE == MODE_FAST) {
+        row_compute_fast_x2<ORDER, BC, LIM>(S, Y, alpha);
+        return;
+    }
     const unsigned full = 0xffffffffu;
     if (Y.tile_has_wall) plant_y_ghosts<BC, VEC>(S.u, Y);  // warp-uniform: first / last column tile only
     float hp[VEC][4], hm[VEC][4];
@@ -275,16 +355,20 @@ __device__ __forceinline__ void ghost_above(RowSlot<VEC> &G, const RowSlot<VEC> 
 template <int BC, int MODE, int VEC, class Ctx>
 __device__ __forceinline__ void finish_o1(const Ctx &X, int i, RowSlot<VEC> &A, RowSlot<VEC> &B, RowSlot<VEC> &C)
 {
-    const Step2DParams &P = *X.P;
-    float uo[VEC][4];
+    if constexpr (VEC == 2 && MODE == MODE_FAST) {
+        finish_o1_fast_x2(X, i, A, B, C);
+    } else {
+        const Step2DParams &P = *X.P;
+        float uo[VEC][4];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) {
-        float s[4], t[4];
-        flux_sum4(B.fp[v], B.fm[v], C.fm[v], A.fp[v], s);
-        apply_first4<MODE>(B.u[v], P.dtdx, s, t);         // base_shll_2d.c:227-230
-        apply_first4<MODE>(t, P.dtdy, B.s1[v], uo[v]);    // base_shll_2d.c:232-235
+        for (int v = 0; v < VEC; v++) {
+            float s[4], t[4];
+            flux_sum4(B.fp[v], B.fm[v], C.fm[v], A.fp[v], s);
+            apply_first4<MODE>(B.u[v], P.dtdx, s, t);         // base_shll_2d.c:227-230
+            apply_first4<MODE>(t, P.dtdy, B.s1[v], uo[v]);    // base_shll_2d.c:232-235
+        }
+        X.template store_row<1>(i, uo);
     }
-    X.template store_row<1>(i, uo);
 }
 
 // ---- order 2: row r has just been computed into D.  A = row r-3 (F+, dF+ valid), B = row r-2 (finished now),
@@ -305,27 +389,35 @@ __device__ __forceinline__ void finish_o2(const Ctx &X, int r, RowSlot<VEC> &A, 
             if (rc == X.wall_lo_row) ghost_below<BC, VEC>(B, C);   // B = row -1
             if (rc == X.wall_hi_row) ghost_above<BC, VEC>(D, C);   // D = row nx
         } else if (rc >= X.first_real_row && rc <= X.last_real_row) {
+            if constexpr (VEC == 2 && MODE == MODE_FAST) {
+                slopes_x_fast_x2<LIM>(B, C, D, P.alpha);
+            } else {
 #pragma unroll
-            for (int v = 0; v < VEC; v++) {
-                limited_slope4<LIM>(B.fp[v], C.fp[v], D.fp[v], P.alpha, C.dfp[v]);
-                limited_slope4<LIM>(B.fm[v], C.fm[v], D.fm[v], P.alpha, C.dfm[v]);
+                for (int v = 0; v < VEC; v++) {
+                    limited_slope4<LIM>(B.fp[v], C.fp[v], D.fp[v], P.alpha, C.dfp[v]);
+                    limited_slope4<LIM>(B.fm[v], C.fm[v], D.fm[v], P.alpha, C.dfm[v]);
+                }
             }
         }
     }
     const int i = r - 2;
     if (i < X.r0) return;  // still filling the window
-    float uo[VEC][4];
+    if constexpr (VEC == 2 && MODE == MODE_FAST) {
+        update_o2_fast_x2(X, i, A, B, C);
+    } else {
+        float uo[VEC][4];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) {
-        float s[4], d[4], t1[4], t2[4], t3[4];
-        flux_sum4(B.fp[v], B.fm[v], C.fm[v], A.fp[v], s);
-        apply_first4<MODE>(B.u[v], P.dtdx, s, t1);                       // 2nd_order_base_shll.c:438
-        slope_sum4(B.dfp[v], B.dfm[v], C.dfm[v], A.dfp[v], d);
-        apply_second4<MODE, POW2>(t1, P.half_dtdx, d, t2);               // :443
-        apply_first4<MODE>(t2, P.dtdy, B.s1[v], t3);                     // :449
-        apply_second4<MODE, POW2>(t3, P.half_dtdy, B.s2[v], uo[v]);      // :454
+        for (int v = 0; v < VEC; v++) {
+            float s[4], d[4], t1[4], t2[4], t3[4];
+            flux_sum4(B.fp[v], B.fm[v], C.fm[v], A.fp[v], s);
+            apply_first4<MODE>(B.u[v], P.dtdx, s, t1);                       // 2nd_order_base_shll.c:438
+            slope_sum4(B.dfp[v], B.dfm[v], C.dfm[v], A.dfp[v], d);
+            apply_second4<MODE, POW2>(t1, P.half_dtdx, d, t2);               // :443
+            apply_first4<MODE>(t2, P.dtdy, B.s1[v], t3);                     // :449
+            apply_second4<MODE, POW2>(t3, P.half_dtdy, B.s2[v], uo[v]);      // :454
+        }
+        X.template store_row<2>(i, uo);
     }
-    X.template store_row<2>(i, uo);
 }
 
 // LDG kernel steps: prefetch one row ahead into the oldest slot's free `u` registers, compute, finish.
