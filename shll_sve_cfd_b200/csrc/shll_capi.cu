@@ -122,11 +122,15 @@ void plan_2d(shll_ctx *c)
     c->key.tma = (g.ny % 4 == 0) && (g.ny >= 32) && env_int("SHLL_TMA", 1) != 0;
     if (c->key.tma) {
         // defaults from the B200 sweep (profiles/r01_sweep_2d.log): order 1 FAST 2 cells per lane, everything else 1
-        if (g.variant <= 0 && env_int("SHLL_VEC", 0) <= 0) vec = (g.order == 1 && g.mode == SHLL_MODE_FAST) ? 2 : 1;
+        if (g.variant <= 0 && env_int("SHLL_VEC", 0) <= 0) vec = (g.mode == SHLL_MODE_FAST) ? 2 : 1;
         if (vec > 2) vec = 2;  // instantiated TMA widths
         while (vec > 1 && (g.ny % (4 * vec) != 0 || g.ny < 32 * vec)) vec >>= 1;
     }
     c->key.vec = vec;
+    // FAST arithmetic, 2 cells per lane: the face-flux accumulate kernel (step2d_acc.cuh); SHLL_ACC=0 keeps the window kernel.
+    c->key.acc = c->key.tma && vec == 2 && g.mode == SHLL_MODE_FAST && env_int("SHLL_ACC", 1) != 0;
+    c->key.acc_cfg = env_int("SHLL_ACC_CFG", 1);
+    if (c->key.acc_cfg < 0 || c->key.acc_cfg > 4) c->key.acc_cfg = 1;
     const int hl = (g.order + vec - 1) / vec;
     const int useful = (32 - 2 * hl) * vec;
     c->ntiles = (g.ny + useful - 1) / useful;
@@ -151,7 +155,7 @@ int make_tensor_maps(shll_ctx *c)
     cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
     if (e != cudaSuccess || fn == nullptr || q != cudaDriverEntryPointSuccess) return -1;
     const shll_config &g = c->cfg;
-    const int R = (g.order == 1) ? 3 : 4;
+    const int R = (g.order == 1 && !c->key.acc) ? 3 : 4;  // rows per box == unroll factor of the kernel's row loop
     for (int b = 0; b < 2; b++) {
         float *base = c->state + (size_t)b * c->ncomp * c->plane_elems;  // plane 0, halo row -2
         cuuint64_t dims[3] = {(cuuint64_t)g.ny, (cuuint64_t)(g.nx + 4), 4};
@@ -172,6 +176,7 @@ int make_tensor_maps(shll_ctx *c)
     if (c->tma_stages > 16) c->tma_stages = 16;
     const size_t stage_stride = ((size_t)4 * R * (32 * c->key.vec + 4) * 4 + 127) & ~(size_t)127;
     c->tma_smem = (size_t)c->tma_stages * stage_stride + 8 * c->tma_stages;
+    if (c->key.acc && g.order == 2 && c->key.acc_cfg >= 2) c->tma_smem += 2048 + 16;  // per-warp stash (step2d_acc.cuh)
     return 0;
 }
 
@@ -297,7 +302,7 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
             plan_2d_fallback(c);
         }
     }
-    snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? "_tma" : "",
+    snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? (c->key.acc ? "_tma_acc" : "_tma") : "",
              g.order, g.bc == SHLL_BC_REFLECT ? "reflect" : "outflow", g.order == 2 ? (g.limiter == SHLL_LIM_MC ? "mc_" : "minmod_") : "",
              g.mode == SHLL_MODE_STRICT ? "strict" : "fast", c->key.pow2 ? "pow2" : "gendt", c->key.vec, c->ntiles, c->nchunks);
 #undef CKC
@@ -423,6 +428,7 @@ int launch_one_step(shll_ctx *c)
         P.dtdx = g.dt_on_dx; P.dtdy = g.dt_on_dy;
         P.half_dtdx = 0.5f * g.dt_on_dx; P.half_dtdy = 0.5f * g.dt_on_dy;
         P.alpha = g.alpha;
+        P.quarter = 0.25f;
         S.edge_warps_lo = S.edge_warps_hi = (unsigned)c->ntiles;
         P.sync = S;
         const int warps = c->ntiles * c->nchunks;
@@ -433,7 +439,8 @@ int launch_one_step(shll_ctx *c)
             T.tmap_global = c->tmap_dev ? c->tmap_dev + in : nullptr;
             T.stages = c->tma_stages;
             dim3 grid(warps);
-            if (g.order == 1) e = launch_step2d_tma_o1(c->key, T, grid, c->tma_smem, c->stream);
+            if (c->key.acc) e = launch_step2d_acc(c->key, T, grid, c->tma_smem, c->stream);
+            else if (g.order == 1) e = launch_step2d_tma_o1(c->key, T, grid, c->tma_smem, c->stream);
             else if (g.mode == SHLL_MODE_STRICT) e = launch_step2d_tma_o2_strict(c->key, T, grid, c->tma_smem, c->stream);
             else e = launch_step2d_tma_o2_fast(c->key, T, grid, c->tma_smem, c->stream);
         } else {

@@ -6,6 +6,7 @@
 #include "step1d.cuh"
 #include "step2d.cuh"
 #include "step2d_tma.cuh"
+#include "step2d_acc.cuh"
 
 namespace shll {
 
@@ -13,6 +14,8 @@ struct KernelKey {
     int order, bc, lim, mode, vec, tform;
     bool pow2;
     bool tma;  // 2D only: TMA-fed kernel (needs ny % 4 == 0)
+    bool acc;  // 2D FAST, TMA, 2 cells per lane: face-flux accumulate kernel (step2d_acc.cuh)
+    int acc_cfg;  // its register cap / stash variant (step2d_acc.cu)
 };
 
 // Each returns cudaSuccess / the launch error; cudaErrorInvalidValue for a combination that was not instantiated.
@@ -22,6 +25,7 @@ cudaError_t launch_step2d_o2_fast(const KernelKey &k, const Step2DParams &p, dim
 cudaError_t launch_step2d_tma_o1(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step2d_tma_o2_strict(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step2d_tma_o2_fast(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
+cudaError_t launch_step2d_acc(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s);
 
 // Persistent register-resident 1D march (cooperative launch; grid = nblocks, one block per SM).

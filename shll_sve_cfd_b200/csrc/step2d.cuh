@@ -33,6 +33,7 @@ struct Step2DParams {
     int lo_wall, hi_wall;  // local row 0 / nx-1 is a physical wall of the global domain
     int ntiles, nchunks;   // column tiles x row chunks = warps of the launch; chunks are balanced (sizes differ by <= 1)
     float dtdx, dtdy, half_dtdx, half_dtdy, alpha;
+    float quarter;         // 0.25f, passed as a parameter so that it lives in a register (step2d_acc.cuh: one-LOP3 sign transfer)
     HaloSync sync;         // multi-GPU only
 };
 

@@ -1,0 +1,461 @@
+// step2d_acc.cuh -- FAST-mode fused 2D step in FACE-FLUX ACCUMULATE form: 2 cells per lane, TMA-fed.
+//
+// Same scheme as step2d.cuh (Compute_F_from_P + Update_U_from_F + Compute_P_from_U of base_shll_2d.c /
+// 2nd_order_base_shll.c), arranged for the issue-bound regime the 2nd-order kernel lives in:
+//
+//  * The reference's two updates per direction (2nd_order_base_shll.c:436-458)
+//        U -= DT_ON_DX*(F+ - F- + Right - Left);  U -= 0.5*DT_ON_DX*(dF+ + dF- - Right_df - Left_df)
+//    are the difference of the reconstructed face fluxes  Phi+ = F+ + dF+/2,  Phi- = F- - dF-/2:
+//        U -= DT_ON_DX*(Phi+[i] - Phi-[i] + Phi-[i+1] - Phi+[i-1]).
+//    The same real-number expression with fewer roundings (this is FAST mode: tolerance-matched, not bit-exact), and it
+//    means a row only has to carry Phi+ of the row behind it and the part of the flux difference that is already known
+//    -- 8 values per component instead of the 4-row x 7-array window of the bit-exact kernel -- so 2 cells per lane fit
+//    in registers without spills and every flux / slope / update operation is a packed FP32x2 instruction on the lane's
+//    cell pair.
+//  * The kernel works with G = -F- = f*Z3 + U*Z2 (and its face value Gamma = G - dG/2 = -Phi-): no negations anywhere,
+//    the signs fold into the operand modifiers of the packed adds.
+//  * minmod(l, r) (2nd_order_base_shll.c:191-201) = (sign(l) + sign(r))/2 * min(|l|, |r|): ONE LOP3 per difference
+//    builds +-0.25 with the sign of the difference, the sum of two of them is the weight w in {+-0.5, 0} and
+//    Phi = F + w*min(|l|,|r|) is one FFMA2.  3 ALU-pipe operations per slope instead of 2 FSETP + 2 FSEL + a product.
+//    (Differs from the reference only when l*r underflows to zero: |slope| < 1e-19.)
+//    MC limiter (base-omp/2nd_order_base_shll.c:317-325): w * min(|l + r|/2, alpha*min(|l|,|r|)).
+//  * Backward differences are reused as the next cell's / next row's forward difference.
+//  * Wall code is compiled out of the hot path twice over: column tiles that touch a y wall run their own instantiation
+//    (WALLTILE), and only the boxes that contain a physical x wall run the EDGE row routine.
+//
+// Rows march as in step2d_tma.cuh: one warp per block, a private shared-memory ring of TMA boxes (4 rows x 68 columns x
+// 4 planes per cp.async.bulk.tensor.3d), conflict-free LDS.64, STG.64 of the finished row; multi-GPU edge rows are
+// stored a second time into the neighbour's halo (halo_sync.cuh).
+#pragma once
+#include "step2d_tma.cuh"
+
+namespace shll {
+
+// (sign(d) ? -q : +q) for q >= 0, and its negative: one LOP3 each when q / nq live in registers.
+__device__ __forceinline__ float sign_times(float d, float q)
+{
+    return __uint_as_float((__float_as_uint(d) & 0x80000000u) | __float_as_uint(q));
+}
+__device__ __forceinline__ float minus_sign_times(float d, float nq)  // nq = -q (or 0)
+{
+    return __uint_as_float((__float_as_uint(d) & 0x80000000u) ^ __float_as_uint(nq));
+}
+// weight of the limited half-slope: +-0.5 where l and r agree in sign, else 0 (q = 0.25 per cell, or 0: no slope)
+__device__ __forceinline__ v2 limiter_weight(v2 l, v2 r, v2 q)
+{
+    return v2add(v2mk(sign_times(l.x, q.x), sign_times(l.y, q.y)), v2mk(sign_times(r.x, q.x), sign_times(r.y, q.y)));
+}
+__device__ __forceinline__ v2 limiter_weight_neg(v2 l, v2 r, v2 nq)
+{
+    return v2add(v2mk(minus_sign_times(l.x, nq.x), minus_sign_times(l.y, nq.y)),
+                 v2mk(minus_sign_times(r.x, nq.x), minus_sign_times(r.y, nq.y)));
+}
+template <int LIM>
+__device__ __forceinline__ v2 limiter_magnitude(v2 l, v2 r, float alpha)
+{
+    v2 m = v2mk(fminf(fabsf(l.x), fabsf(r.x)), fminf(fabsf(l.y), fabsf(r.y)));
+    if (LIM == LIM_MC) {
+        const v2 c = v2mul(v2bc(0.5f), v2add(l, r));
+        const v2 am = v2mul(v2bc(alpha), m);
+        m = v2mk(fminf(fabsf(c.x), am.x), fminf(fabsf(c.y), am.y));
+    }
+    return m;
+}
+
+// cell_flux_2d_fast_x2 with the minus fluxes un-negated: gm = -F-, hgm = -H-.
+__device__ __forceinline__ void cell_flux_2d_fast_x2g(const v2 (&u)[4], v2 (&fp)[4], v2 (&gm)[4], v2 (&hp)[4], v2 (&hgm)[4])
+{
+    const v2 r = v2rcp_newton(u[0]);
+    const v2 ux = v2mul(u[1], r), uy = v2mul(u[2], r);
+    const v2 k = v2fma(ux, ux, v2mul(uy, uy));
+    const v2 T = v2mul(v2fma(v2bc(-0.5f), k, v2mul(u[3], r)), v2bc(1.0f / SHLL_CV_F));
+    const v2 g = v2mul(v2bc(SHLL_GAMMA_F), T);
+    const v2 inv_a = v2rsqrt_newton(g);
+    const v2 a = v2mul(g, inv_a);
+    const v2 P = v2mul(u[0], T);
+    const v2 eP = v2add(u[3], P);
+    v2 f[4], h[4];
+    f[0] = u[1]; f[1] = v2fma(u[1], ux, P); f[2] = v2mul(u[1], uy); f[3] = v2mul(ux, eP);
+    h[0] = u[2]; h[1] = v2mul(u[2], ux); h[2] = v2fma(u[2], uy, P); h[3] = v2mul(uy, eP);
+    const v2 ha = v2mul(v2bc(0.5f), a);
+    {
+        const v2 M = v2mul(ux, inv_a);
+        const v2 z1 = v2fma(v2bc(0.5f), M, v2bc(0.5f)), z3 = v2fma(v2bc(0.5f), M, v2bc(-0.5f));
+        const v2 z2 = v2mul(ha, v2fma(v2neg(M), M, v2bc(1.0f)));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const v2 uz = v2mul(u[c], z2);
+            fp[c] = v2fma(f[c], z1, uz);
+            gm[c] = v2fma(f[c], z3, uz);
+        }
+    }
+    {
+        const v2 M = v2mul(uy, inv_a);
+        const v2 z1 = v2fma(v2bc(0.5f), M, v2bc(0.5f)), z3 = v2fma(v2bc(0.5f), M, v2bc(-0.5f));
+        const v2 z2 = v2mul(ha, v2fma(v2neg(M), M, v2bc(1.0f)));
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            const v2 uz = v2mul(u[c], z2);
+            hp[c] = v2fma(h[c], z1, uz);
+            hgm[c] = v2fma(h[c], z3, uz);
+        }
+    }
+}
+
+// Wall ghost fluxes at an x wall, in (F+, G = -F-) form.  REFLECT (base_shll_2d.c:152-155,168-171): the ghost flux is the
+// cell's own opposite split flux, + for the wall-normal momentum component (k == 1) and - otherwise.  OUTFLOW
+// (2nd_order_base_shll.c:216-219,243-246): the cell's own same split flux.
+template <int BC>
+__device__ __forceinline__ v2 ghost_fp_below(v2 fp, v2 g, int k)   // F+ of the ghost row below a wall row
+{
+    if (BC == BC_REFLECT) return (k == 1) ? v2neg(g) : g;   // (k==1) ? F- : -F-
+    return fp;
+}
+template <int BC>
+__device__ __forceinline__ v2 ghost_g_above(v2 fp, v2 g, int k)    // G = -F- of the ghost row above a wall row
+{
+    if (BC == BC_REFLECT) return (k == 1) ? v2neg(fp) : fp;  // F-ghost = (k==1) ? F+ : -F+
+    return g;
+}
+
+// What a warp carries from row to row (per conserved component, per cell pair).  The x update of row i is applied in one
+// piece, U'' = U' - DT_ON_DX*(D[i] - Gamma[i+1]) with D[i] = (Phi+[i] - Phi+[i-1]) + Gamma[i]: the bracket is a small
+// difference (exactly zero in a uniform gas, like the reference's sum), so a gas at rest stays bit-for-bit at rest.
+// (Applying D[i] and Gamma[i+1] to U in two steps was measured 5-10x noisier against the reference: every step then
+// rounds U - DT_ON_DX*Gamma, which is not small, everywhere in the domain.)
+template <int ORDER>
+struct AccState {
+    v2 fpP[4];   // F+ of the previous row
+    v2 D[4];     // D of row r-ORDER
+    v2 accB[4];  // row r-ORDER: state minus its y-direction update
+    v2 gP[4];    // order 2: G of the previous row
+    v2 ep[4];    //          F+[r-1] - F+[r-2]
+    v2 em[4];    //          G[r-1] - G[r-2]
+    v2 PhiP[4];  //          Phi+ of row r-2
+    v2 acc0[4];  //          row r-1: state minus its y-direction update
+};
+
+struct AccRows {   // warp-uniform row bookkeeping
+    int r0, r1;                    // rows [r0, r1) are stored by this warp
+    int rmin, rmax;                // rows that exist in memory
+    int wall_lo_row, wall_hi_row;  // 0 / nx-1 where that row is a physical wall, else a value no row takes
+    int noslope_lo, noslope_hi;    // rows strictly between them get limited x slopes
+    float quarter, nquarter;       // 0.25f / -0.25f from kernel parameters: registers, so the sign transfer is one LOP3
+    uint32_t stash;                // STASH: shared address of this lane's slot in the 2-row stash of (state - y update)
+};
+
+// Order 2 keeps `state minus y update` of rows r-1 and r-2 until their x update completes.  With STASH these 16 registers
+// live in a per-warp shared-memory stash instead (2 rows x 4 components x 32 lanes x 8 bytes; row r uses slot r & 1):
+// 4 STS.64 + 4 LDS.64 per row buy one more resident warp per scheduler.
+__device__ __forceinline__ v2 stash_load(uint32_t a)
+{
+    v2 v;
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void stash_store(uint32_t a, v2 v)
+{
+    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// Split fluxes of row r and its state minus the y-direction update (accN).
+template <int ORDER, int BC, int LIM, bool WALLTILE>
+__device__ __forceinline__ void acc_row_y(const YEdge<2> &Y, const Step2DParams &P, const AccRows &W, float (&uin)[2][4],
+                                          v2 (&fp)[4], v2 (&g)[4], v2 (&accN)[4])
+{
+    const unsigned full = 0xffffffffu;
+    if (WALLTILE) {
+        // y walls as ghost STATES (see plant_y_ghosts): mirrored / copied wall cell just outside the domain, and a gas at
+        // rest in the cells further out (their values are never used, they only have to stay finite).
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const float from_hi = __shfl_down_sync(full, uin[0][k], 1);
+            const float from_lo = __shfl_up_sync(full, uin[1][k], 1);
+            const float sgn = (BC == BC_REFLECT && k == 2) ? -1.0f : 1.0f;
+            const float rest = (k == 0 || k == 3) ? 1.0f : 0.0f;
+            if (Y.outside[0]) uin[0][k] = rest;
+            if (Y.outside[1]) uin[1][k] = rest;
+            if (Y.ghost_lo) uin[1][k] = sgn * from_hi;
+            if (Y.ghost_hi) uin[0][k] = sgn * from_lo;
+        }
+    }
+    const v2 u[4] = {v2mk(uin[0][0], uin[1][0]), v2mk(uin[0][1], uin[1][1]), v2mk(uin[0][2], uin[1][2]), v2mk(uin[0][3], uin[1][3])};
+    v2 hp[4], hg[4];
+    cell_flux_2d_fast_x2g(u, fp, g, hp, hg);
+    // slopes vanish in wall cells and beyond (2nd_order_base_shll.c:292-300,314-322,396-399,412-415)
+    v2 q = v2bc(W.quarter), nq = v2bc(W.nquarter);
+    if (WALLTILE) {
+        q = v2mk(Y.y_inner[0] ? W.quarter : 0.0f, Y.y_inner[1] ? W.quarter : 0.0f);
+        nq = v2mk(Y.y_inner[0] ? W.nquarter : 0.0f, Y.y_inner[1] ? W.nquarter : 0.0f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        v2 ysum;
+        if (ORDER == 1) {
+            const v2 hp_lo = v2mk(__shfl_up_sync(full, hp[k].y, 1), hp[k].x);    // H+ of cells j-1 (Bottom)
+            const v2 hg_hi = v2mk(hg[k].y, __shfl_down_sync(full, hg[k].x, 1));  // -H- of cells j+1 (-Top)
+            ysum = v2sub(v2sub(v2add(hp[k], hg[k]), hg_hi), hp_lo);              // base_shll_2d.c:232-235
+        } else {
+            // backward differences d[j] = H[j] - H[j-1]; the forward difference of cell j is d[j+1]
+            const v2 dlp = v2sub(hp[k], v2mk(__shfl_up_sync(full, hp[k].y, 1), hp[k].x));
+            const v2 dlm = v2sub(hg[k], v2mk(__shfl_up_sync(full, hg[k].y, 1), hg[k].x));
+            const v2 drp = v2mk(dlp.y, __shfl_down_sync(full, dlp.x, 1));
+            const v2 drm = v2mk(dlm.y, __shfl_down_sync(full, dlm.x, 1));
+            const v2 psi = v2fma(limiter_weight(dlp, drp, q), limiter_magnitude<LIM>(dlp, drp, P.alpha), hp[k]);      // H+ + dH+/2
+            const v2 gam = v2fma(limiter_weight_neg(dlm, drm, nq), limiter_magnitude<LIM>(dlm, drm, P.alpha), hg[k]);  // -(H- - dH-/2)
+            const v2 psi_lo = v2mk(__shfl_up_sync(full, psi.y, 1), psi.x);
+            const v2 gam_hi = v2mk(gam.y, __shfl_down_sync(full, gam.x, 1));
+            ysum = v2sub(v2sub(v2add(psi, gam), gam_hi), psi_lo);
+        }
+        accN[k] = v2fma(v2bc(-P.dtdy), ysum, u[k]);
+    }
+}
+
+// Finished row i leaves: local store, and for the multi-GPU edge rows a second store into the neighbour's halo (kept
+// out of line: it runs for ORDER rows per slab side only).
+static __device__ __noinline__ void acc_store_peer(const Step2DParams *P, bool lo, int pidx, v2 o0, v2 o1, v2 o2, v2 o3)
+{
+    const v2 o[4] = {o0, o1, o2, o3};
+#pragma unroll
+    for (int k = 0; k < 4; k++) *reinterpret_cast<float2 *>((lo ? P->lo_peer[k] : P->hi_peer[k]) + pidx) = o[k];
+}
+template <class Ctx>
+__device__ __forceinline__ void acc_store(const Ctx &X, int i, const v2 (&o)[4])
+{
+    if (X.owner) {
+        const int idx = i * X.ny + X.j0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) *reinterpret_cast<float2 *>(X.P->out[k] + idx) = o[k];
+        if (i < X.peer_lo_end || i >= X.peer_hi_begin) {
+            const bool lo = i < X.peer_lo_end;
+            acc_store_peer(X.P, lo, lo ? idx : (i - X.peer_hi_begin) * X.ny + X.j0, o[0], o[1], o[2], o[3]);
+        }
+    }
+}
+
+// One step of the march: row r arrives, row r-ORDER leaves.  EDGE = this box may contain a physical x wall.
+template <int ORDER, int BC, int LIM, bool WALLTILE, bool EDGE, bool STASH, class Ctx>
+__device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState<ORDER> &S, int r, float (&uin)[2][4])
+{
+    const Step2DParams &P = *X.P;
+    const v2 mdtdx = v2bc(-P.dtdx);
+    v2 fp[4], g[4], accN[4], o[4];
+    if (ORDER == 1) {
+        if (EDGE && (r < W.rmin || r > W.rmax)) return;  // beyond a wall: the wall row was finished when it was computed
+        acc_row_y<1, BC, LIM, WALLTILE>(X.Y, P, W, uin, fp, g, accN);
+        if (EDGE && r == W.wall_lo_row) {  // Left of row 0 = its own wall flux (base_shll_2d.c:152-155)
+#pragma unroll
+            for (int k = 0; k < 4; k++) S.fpP[k] = ghost_fp_below<BC>(fp[k], g[k], k);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; k++) o[k] = v2fma(mdtdx, v2sub(S.D[k], g[k]), S.accB[k]);  // Right of row r-1 = F-[r] = -G[r]
+        if (r - 1 >= W.r0) acc_store(X, r - 1, o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            S.D[k] = v2add(v2sub(fp[k], S.fpP[k]), g[k]);
+            S.accB[k] = accN[k];
+            S.fpP[k] = fp[k];
+        }
+        if (EDGE && r == W.wall_hi_row && r < W.r1) {  // Right of row nx-1 = its own wall flux (base_shll_2d.c:168-171)
+#pragma unroll
+            for (int k = 0; k < 4; k++) o[k] = v2fma(mdtdx, v2sub(S.D[k], ghost_g_above<BC>(fp[k], g[k], k)), accN[k]);
+            acc_store(X, r, o);
+        }
+    } else {
+        if (EDGE && (r < W.rmin || r > W.rmax)) {
+            // Row r does not exist.  r == nx above a wall: finish rows nx-2 and nx-1 here -- the wall row is first order
+            // (2nd_order_base_shll.c:248-256) and its Right flux is its own wall flux, no slope beyond (:243-246,378-381).
+            if (r == W.wall_hi_row + 1) {
+                if (STASH) {
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        S.accB[k] = stash_load(W.stash + ((r & 1) << 10) + k * 256);        // row r-2
+                        S.acc0[k] = stash_load(W.stash + (((r + 1) & 1) << 10) + k * 256);  // row r-1
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) o[k] = v2fma(mdtdx, v2sub(S.D[k], S.gP[k]), S.accB[k]);
+                if (r - 2 >= W.r0) acc_store(X, r - 2, o);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const v2 d1 = v2add(v2sub(S.fpP[k], S.PhiP[k]), S.gP[k]);
+                    o[k] = v2fma(mdtdx, v2sub(d1, ghost_g_above<BC>(S.fpP[k], S.gP[k], k)), S.acc0[k]);
+                }
+                if (r - 1 >= W.r0) acc_store(X, r - 1, o);
+            }
+            return;
+        }
+        acc_row_y<2, BC, LIM, WALLTILE>(X.Y, P, W, uin, fp, g, accN);
+        const int rc = r - 1;  // the row whose face fluxes are completed by this step
+        // wall rows are first order (2nd_order_base_shll.c:226-234,248-256): zero weight instead of a branch
+        float qx = W.quarter, nqx = W.nquarter;
+        if (EDGE && !(rc > W.noslope_lo && rc < W.noslope_hi)) qx = nqx = 0.0f;
+        v2 php[4], gam[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const v2 eNp = v2sub(fp[k], S.fpP[k]), eNm = v2sub(g[k], S.gP[k]);
+            php[k] = v2fma(limiter_weight(S.ep[k], eNp, v2bc(qx)), limiter_magnitude<LIM>(S.ep[k], eNp, P.alpha), S.fpP[k]);      // :268-276
+            gam[k] = v2fma(limiter_weight_neg(S.em[k], eNm, v2bc(nqx)), limiter_magnitude<LIM>(S.em[k], eNm, P.alpha), S.gP[k]);
+            S.ep[k] = eNp;
+            S.em[k] = eNm;
+        }
+        if (EDGE && rc == W.wall_lo_row) {  // Left of row 0 = its own wall flux, no slope beyond the wall (:216-219,362-365)
+#pragma unroll
+            for (int k = 0; k < 4; k++) S.PhiP[k] = ghost_fp_below<BC>(S.fpP[k], S.gP[k], k);
+        }
+        const uint32_t slot = W.stash + ((r & 1) << 10);  // holds row r-2, then row r
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const v2 yB = STASH ? stash_load(slot + k * 256) : S.accB[k];
+            o[k] = v2fma(mdtdx, v2sub(S.D[k], gam[k]), yB);  // Right of row r-2 = Phi-[r-1] = -Gamma[r-1]
+        }
+        if (r - 2 >= W.r0) acc_store(X, r - 2, o);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            S.D[k] = v2add(v2sub(php[k], S.PhiP[k]), gam[k]);
+            if (STASH) {
+                stash_store(slot + k * 256, accN[k]);
+            } else {
+                S.accB[k] = S.acc0[k];
+                S.acc0[k] = accN[k];
+            }
+            S.PhiP[k] = php[k];
+            S.fpP[k] = fp[k];
+            S.gP[k] = g[k];
+        }
+    }
+}
+
+// read row `within` (run-time) of the box sitting in `stage`: 2 cells per lane
+template <class Ctx>
+__device__ __forceinline__ void acc_read_row(const Ctx &X, int stage, int within, float (&u)[2][4])
+{
+    const uint32_t a = X.ring + Ctx::STAGE_STRIDE * stage + within * Ctx::ROW_BYTES + X.lane_off;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(u[0][k]), "=f"(u[1][k]) : "r"(a + k * Ctx::PLANE_BYTES));
+}
+
+template <int ORDER, int BC, int LIM, bool WALLTILE, bool STASH, class Ctx>
+__device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, int rlast, int lane)
+{
+    AccState<ORDER> S;
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+        S.fpP[k] = S.D[k] = S.accB[k] = S.gP[k] = S.ep[k] = S.em[k] = S.PhiP[k] = S.acc0[k] = v2bc(0.0f);
+    int stage = 0;
+    uint32_t parity = 0;
+    float uin[2][4];
+    const int nx = X.P->nx;
+    for (int box = 0; box < X.nboxes; box++) {
+        const int r = rbeg + 4 * box;
+        mbar_wait(X.bars + 8u * stage, parity);
+        // a box needs the EDGE routine if one of its rows is missing, is a wall row, or completes / follows a wall row
+        const bool edge = (r <= 1 && X.P->lo_wall) || (r + 3 >= nx - 1 && X.P->hi_wall) || (r + 3 > rlast);
+        if (edge) {
+#pragma unroll 1
+            for (int w = 0; w < 4; w++) {
+                if (r + w > rlast) break;
+                acc_read_row(X, stage, w, uin);
+                acc_row<ORDER, BC, LIM, WALLTILE, true, STASH>(X, W, S, r + w, uin);
+            }
+        } else {
+            X.template read_row<0>(stage, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r, uin);
+            X.template read_row<1>(stage, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r + 1, uin);
+            X.template read_row<2>(stage, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r + 2, uin);
+            X.template read_row<3>(stage, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r + 3, uin);
+        }
+        // the box has been fully read: refill its stage, move on
+        __syncwarp();
+        if (lane == 0 && box + X.stages < X.nboxes) X.arm(box + X.stages, stage);
+        stage++;
+        if (stage == X.stages) { stage = 0; parity ^= 1u; }
+    }
+}
+
+// MINB = resident warps per SM the register allocation is capped for (launch bounds); STASH see above.
+template <int ORDER, int BC, int LIM, int MINB, bool STASH>
+__global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_constant__ Step2DTmaParams T)
+{
+    constexpr int R = 4, VEC = 2, HL = 1;
+    constexpr int USEFUL = (32 - 2 * HL) * VEC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Step2DParams &P = T.base;
+    const int lane = threadIdx.x;
+    const int gw = blockIdx.x;
+    const int tile = gw % P.ntiles;
+    int chunk = gw / P.ntiles;
+    if (P.nchunks > 2) chunk = (chunk == 0) ? 0 : (chunk == 1 ? P.nchunks - 1 : chunk - 1);  // edge chunks first
+
+    TmaCtx<VEC, R> X;
+    X.P = &P;
+    X.T = &T;
+    const int nx = P.nx;
+    X.ny = P.ny;
+    const int xs = tile * USEFUL - HL * VEC;
+    X.x0 = xs & ~3;
+    X.j0 = xs + lane * VEC;
+    X.owner = (lane >= HL) && (lane < 32 - HL) && (X.j0 < X.ny);
+    X.Y.tile_has_wall = (tile == 0) || (tile == P.ntiles - 1);
+    X.Y.ghost_lo = (X.j0 + VEC - 1 == -1);
+    X.Y.ghost_hi = (X.j0 == X.ny);
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        X.Y.y_inner[v] = (X.j0 + v > 0 && X.j0 + v < X.ny - 1);
+        X.Y.outside[v] = (X.j0 + v < 0 || X.j0 + v >= X.ny);
+    }
+    X.r0 = (int)(((long)chunk * nx) / P.nchunks);
+    X.r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
+    const int never = -(1 << 30);
+    X.wall_lo_row = X.wall_hi_row = X.first_real_row = X.last_real_row = never;  // (window-kernel fields, unused here)
+    X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? ORDER : 0;
+    X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - ORDER : 0x7fffffff;
+    AccRows W;
+    W.r0 = X.r0;
+    W.r1 = X.r1;
+    W.rmin = P.lo_wall ? 0 : -2;
+    W.rmax = P.hi_wall ? nx - 1 : nx + 1;
+    W.wall_lo_row = P.lo_wall ? 0 : never;
+    W.wall_hi_row = P.hi_wall ? nx - 1 : never;
+    W.noslope_lo = P.lo_wall ? 0 : never;
+    W.noslope_hi = P.hi_wall ? nx - 1 : -never;
+    W.quarter = P.quarter;
+    W.nquarter = -P.quarter;
+    W.stash = 0;
+    const bool touch_lo = (X.r0 < ORDER), touch_hi = (X.r1 > nx - ORDER);
+    if (P.sync.enabled) {
+        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
+        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
+    }
+
+    const int rbeg = X.r0 - ORDER;
+    const int rlast = X.r1 - 1 + ORDER;
+    X.stages = T.stages;
+    X.ring = smem_u32(smem);
+    X.bars = X.ring + TmaCtx<VEC, R>::STAGE_STRIDE * X.stages;
+    X.lane_off = (uint32_t)(xs - X.x0 + lane * VEC) * 4u;
+    X.ybase = rbeg + 2;
+    X.nboxes = (rlast - rbeg) / R + 1;
+    if (STASH) W.stash = ((X.bars + 8u * X.stages + 15u) & ~15u) + 8u * lane;  // host adds 2 KB + 16 to the dynamic smem
+    if (lane == 0) {
+        for (int s = 0; s < X.stages; s++) mbar_init(X.bars + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int b = 0; b < X.stages && b < X.nboxes; b++) X.arm(b, b);
+    }
+    __syncwarp();
+
+    if (X.Y.tile_has_wall) acc_march<ORDER, BC, LIM, true, STASH>(X, W, rbeg, rlast, lane);
+    else acc_march<ORDER, BC, LIM, false, STASH>(X, W, rbeg, rlast, lane);
+
+    if (P.sync.enabled) {
+        if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);
+        if (touch_hi) halo_arrive(P.sync, P.sync.cnt_hi, P.sync.edge_warps_hi, P.sync.sig_hi);
+    }
+}
+
+}  // namespace shll
