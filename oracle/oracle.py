@@ -127,6 +127,31 @@ def run(cfg: Cfg, u: np.ndarray, nsteps: int) -> np.ndarray:
     return out
 
 
+def run_fma_contracted(cfg: Cfg, u: np.ndarray, nsteps: int):
+    """The same restatement built the way an FMA machine builds the reference by default (gcc -O2 -mfma
+    -ffp-contract=fast, i.e. what Graviton gives base-c): the size of the difference between its result and run()'s is
+    the reference's OWN sensitivity to contraction on that problem, which is the scale the FAST-mode tolerance of the CUDA
+    path is stated against (tests/test_oracle_golden.py).  Returns None on a CPU without FMA."""
+    try:
+        with open("/proc/cpuinfo") as f:
+            if " fma" not in f.read():
+                return None
+    except OSError:
+        return None
+    path = os.path.join(HERE, "libshll_oracle_fma.so")
+    src = os.path.join(HERE, "shll_oracle.c")
+    if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+        subprocess.check_call(["gcc", "-O2", "-mfma", "-ffp-contract=fast", "-fno-fast-math", "-fopenmp", "-shared", "-fPIC",
+                               "-o", path, src, "-lm"])
+    L = C.CDLL(path)
+    L.shll_oracle_run.argtypes = [C.POINTER(Cfg), C.POINTER(C.c_void_p), C.c_long]
+    out = np.ascontiguousarray(u, dtype=np.float32).copy()
+    rc = L.shll_oracle_run(C.byref(cfg), _ptrs(out), int(nsteps))
+    if rc:
+        raise RuntimeError(f"shll_oracle_run (fma build) rc={rc}")
+    return out
+
+
 def count_steps(dt: float, total: float) -> int:
     return int(lib().shll_oracle_count_steps(np.float32(dt), np.float32(total)))
 

@@ -134,7 +134,7 @@ void plan_2d(shll_ctx *c)
     const int hl = (g.order + vec - 1) / vec;
     const int useful = (32 - 2 * hl) * vec;
     c->ntiles = (g.ny + useful - 1) / useful;
-    int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? (g.order == 1 ? 24 : 64) : 64);
+    int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? (g.order == 1 ? (c->key.acc ? 18 : 24) : 64) : 64);  // B200 sweeps (profiles/)
     if (rpc < 2) rpc = 2;
     int nchunks = (g.nx + rpc - 1) / rpc;
     if (nchunks < 1) nchunks = 1;
@@ -171,12 +171,12 @@ int make_tensor_maps(shll_ctx *c)
         if (cudaMalloc(&c->tmap_dev, 2 * sizeof(CUtensorMap)) != cudaSuccess) return -2;
         if (cudaMemcpy(c->tmap_dev, c->tmap, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
     }
-    c->tma_stages = env_int("SHLL_TMA_STAGES", c->key.vec == 2 ? 3 : 4);
+    c->tma_stages = env_int("SHLL_TMA_STAGES", c->key.acc ? 2 : (c->key.vec == 2 ? 3 : 4));
     if (c->tma_stages < 2) c->tma_stages = 2;
     if (c->tma_stages > 16) c->tma_stages = 16;
     const size_t stage_stride = ((size_t)4 * R * (32 * c->key.vec + 4) * 4 + 127) & ~(size_t)127;
     c->tma_smem = (size_t)c->tma_stages * stage_stride + 8 * c->tma_stages;
-    if (c->key.acc && g.order == 2 && c->key.acc_cfg >= 2) c->tma_smem += 2048 + 16;  // per-warp stash (step2d_acc.cuh)
+    if (c->key.acc && g.order == 2 && c->key.acc_cfg >= 2) c->tma_smem += (c->key.acc_cfg == 4 ? 2048 : 4096) + 16;  // per-warp stash (step2d_acc.cuh)
     return 0;
 }
 

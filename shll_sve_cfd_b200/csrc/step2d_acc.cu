@@ -3,23 +3,23 @@
 
 namespace shll {
 
-template <int ORDER, int BC, int LIM, int MINB, bool STASH>
+template <int ORDER, int BC, int LIM, int MINB, int STASH>
 static cudaError_t go(const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
 {
     step2d_acc_kernel<ORDER, BC, LIM, MINB, STASH><<<grid, 32, smem, s>>>(p);
     return cudaGetLastError();
 }
 
-// order 2: register cap / stash chosen by the host (KernelKey::acc_cfg: 0 = 8 warps per SM, 1 = 12, 2 = 12 + stash, 3 = 13 + stash, 4 = 14 + stash)
+// order 2: register cap (resident warps per SM) / stash level chosen by the host, KernelKey::acc_cfg
 template <int BC, int LIM>
 static cudaError_t go_o2(int cfg, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
 {
     switch (cfg) {
-    case 0: return go<2, BC, LIM, 8, false>(p, grid, smem, s);
-    case 1: return go<2, BC, LIM, 12, false>(p, grid, smem, s);
-    case 2: return go<2, BC, LIM, 12, true>(p, grid, smem, s);
-    case 3: return go<2, BC, LIM, 13, true>(p, grid, smem, s);
-    case 4: return go<2, BC, LIM, 14, true>(p, grid, smem, s);
+    case 0: return go<2, BC, LIM, 8, 0>(p, grid, smem, s);
+    case 1: return go<2, BC, LIM, 12, 0>(p, grid, smem, s);
+    case 2: return go<2, BC, LIM, 14, 2>(p, grid, smem, s);
+    case 3: return go<2, BC, LIM, 16, 2>(p, grid, smem, s);
+    case 4: return go<2, BC, LIM, 14, 1>(p, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -28,8 +28,8 @@ cudaError_t launch_step2d_acc(const KernelKey &k, const Step2DTmaParams &p, dim3
 {
     if (k.mode != MODE_FAST || k.vec != 2) return cudaErrorInvalidValue;
     if (k.order == 1) {
-        if (k.bc == BC_REFLECT) return go<1, BC_REFLECT, LIM_MINMOD, 16, false>(p, grid, smem, s);
-        if (k.bc == BC_OUTFLOW) return go<1, BC_OUTFLOW, LIM_MINMOD, 16, false>(p, grid, smem, s);
+        if (k.bc == BC_REFLECT) return go<1, BC_REFLECT, LIM_MINMOD, 16, 0>(p, grid, smem, s);
+        if (k.bc == BC_OUTFLOW) return go<1, BC_OUTFLOW, LIM_MINMOD, 16, 0>(p, grid, smem, s);
     } else {
         if (k.bc == BC_REFLECT && k.lim == LIM_MINMOD) return go_o2<BC_REFLECT, LIM_MINMOD>(k.acc_cfg, p, grid, smem, s);
         if (k.bc == BC_REFLECT && k.lim == LIM_MC) return go_o2<BC_REFLECT, LIM_MC>(k.acc_cfg, p, grid, smem, s);

@@ -145,8 +145,9 @@ struct AccRows {   // warp-uniform row bookkeeping
 };
 
 // Order 2 keeps `state minus y update` of rows r-1 and r-2 until their x update completes.  With STASH these 16 registers
-// live in a per-warp shared-memory stash instead (2 rows x 4 components x 32 lanes x 8 bytes; row r uses slot r & 1):
-// 4 STS.64 + 4 LDS.64 per row buy one more resident warp per scheduler.
+// live in a per-warp shared-memory stash instead (2 rows x 4 components x 32 lanes x 8 bytes; row r uses slot r & 1);
+// STASH level 2 also keeps the backward differences of F+ and G there (16 more registers).  8 / 24 LDS.64 + STS.64 per row
+// in exchange for more resident warps per scheduler.
 __device__ __forceinline__ v2 stash_load(uint32_t a)
 {
     v2 v;
@@ -192,20 +193,20 @@ __device__ __forceinline__ void acc_row_y(const YEdge<2> &Y, const Step2DParams 
     for (int k = 0; k < 4; k++) {
         v2 ysum;
         if (ORDER == 1) {
-            const v2 hp_lo = v2mk(__shfl_up_sync(full, hp[k].y, 1), hp[k].x);    // H+ of cells j-1 (Bottom)
-            const v2 hg_hi = v2mk(hg[k].y, __shfl_down_sync(full, hg[k].x, 1));  // -H- of cells j+1 (-Top)
-            ysum = v2sub(v2sub(v2add(hp[k], hg[k]), hg_hi), hp_lo);              // base_shll_2d.c:232-235
+            // (H+ - H-) - (H+ of cell j-1 - H- of cell j+1), base_shll_2d.c:232-235; the neighbour terms as scalar sums so that
+            // no register pair has to be formed around the shuffled values
+            const float up = __shfl_up_sync(full, hp[k].y, 1), dn = __shfl_down_sync(full, hg[k].x, 1);
+            ysum = v2sub(v2add(hp[k], hg[k]), v2mk(fadd(hg[k].y, up), fadd(dn, hp[k].x)));
         } else {
             // backward differences d[j] = H[j] - H[j-1]; the forward difference of cell j is d[j+1]
-            const v2 dlp = v2sub(hp[k], v2mk(__shfl_up_sync(full, hp[k].y, 1), hp[k].x));
-            const v2 dlm = v2sub(hg[k], v2mk(__shfl_up_sync(full, hg[k].y, 1), hg[k].x));
+            const v2 dlp = v2mk(fsub(hp[k].x, __shfl_up_sync(full, hp[k].y, 1)), fsub(hp[k].y, hp[k].x));
+            const v2 dlm = v2mk(fsub(hg[k].x, __shfl_up_sync(full, hg[k].y, 1)), fsub(hg[k].y, hg[k].x));
             const v2 drp = v2mk(dlp.y, __shfl_down_sync(full, dlp.x, 1));
             const v2 drm = v2mk(dlm.y, __shfl_down_sync(full, dlm.x, 1));
             const v2 psi = v2fma(limiter_weight(dlp, drp, q), limiter_magnitude<LIM>(dlp, drp, P.alpha), hp[k]);      // H+ + dH+/2
             const v2 gam = v2fma(limiter_weight_neg(dlm, drm, nq), limiter_magnitude<LIM>(dlm, drm, P.alpha), hg[k]);  // -(H- - dH-/2)
-            const v2 psi_lo = v2mk(__shfl_up_sync(full, psi.y, 1), psi.x);
-            const v2 gam_hi = v2mk(gam.y, __shfl_down_sync(full, gam.x, 1));
-            ysum = v2sub(v2sub(v2add(psi, gam), gam_hi), psi_lo);
+            const float up = __shfl_up_sync(full, psi.y, 1), dn = __shfl_down_sync(full, gam.x, 1);
+            ysum = v2sub(v2add(psi, gam), v2mk(fadd(gam.y, up), fadd(dn, psi.x)));
         }
         accN[k] = v2fma(v2bc(-P.dtdy), ysum, u[k]);
     }
@@ -232,9 +233,21 @@ __device__ __forceinline__ void acc_store(const Ctx &X, int i, const v2 (&o)[4])
         }
     }
 }
+// Interior boxes: the row is stored unconditionally by the owner lanes, no peer copy.
+// (Four predicated STG.64 in one asm block were tried instead of the branch: all four addresses and values live at once
+// cost 40+ registers of pressure and spills.)
+template <class Ctx>
+__device__ __forceinline__ void acc_store_owned(const Ctx &X, int i, const v2 (&o)[4])
+{
+    if (X.owner) {
+        const int idx = i * X.ny + X.j0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) *reinterpret_cast<float2 *>(X.P->out[k] + idx) = o[k];
+    }
+}
 
 // One step of the march: row r arrives, row r-ORDER leaves.  EDGE = this box may contain a physical x wall.
-template <int ORDER, int BC, int LIM, bool WALLTILE, bool EDGE, bool STASH, class Ctx>
+template <int ORDER, int BC, int LIM, bool WALLTILE, bool EDGE, int STASH, class Ctx>
 __device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState<ORDER> &S, int r, float (&uin)[2][4])
 {
     const Step2DParams &P = *X.P;
@@ -249,7 +262,7 @@ __device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) o[k] = v2fma(mdtdx, v2sub(S.D[k], g[k]), S.accB[k]);  // Right of row r-1 = F-[r] = -G[r]
-        if (r - 1 >= W.r0) acc_store(X, r - 1, o);
+        if (EDGE) { if (r - 1 >= W.r0) acc_store(X, r - 1, o); } else acc_store_owned(X, r - 1, o);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             S.D[k] = v2add(v2sub(fp[k], S.fpP[k]), g[k]);
@@ -294,10 +307,17 @@ __device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             const v2 eNp = v2sub(fp[k], S.fpP[k]), eNm = v2sub(g[k], S.gP[k]);
-            php[k] = v2fma(limiter_weight(S.ep[k], eNp, v2bc(qx)), limiter_magnitude<LIM>(S.ep[k], eNp, P.alpha), S.fpP[k]);      // :268-276
-            gam[k] = v2fma(limiter_weight_neg(S.em[k], eNm, v2bc(nqx)), limiter_magnitude<LIM>(S.em[k], eNm, P.alpha), S.gP[k]);
-            S.ep[k] = eNp;
-            S.em[k] = eNm;
+            const v2 ep = (STASH >= 2) ? stash_load(W.stash + 2048 + k * 256) : S.ep[k];
+            const v2 em = (STASH >= 2) ? stash_load(W.stash + 3072 + k * 256) : S.em[k];
+            php[k] = v2fma(limiter_weight(ep, eNp, v2bc(qx)), limiter_magnitude<LIM>(ep, eNp, P.alpha), S.fpP[k]);      // :268-276
+            gam[k] = v2fma(limiter_weight_neg(em, eNm, v2bc(nqx)), limiter_magnitude<LIM>(em, eNm, P.alpha), S.gP[k]);
+            if (STASH >= 2) {
+                stash_store(W.stash + 2048 + k * 256, eNp);
+                stash_store(W.stash + 3072 + k * 256, eNm);
+            } else {
+                S.ep[k] = eNp;
+                S.em[k] = eNm;
+            }
         }
         if (EDGE && rc == W.wall_lo_row) {  // Left of row 0 = its own wall flux, no slope beyond the wall (:216-219,362-365)
 #pragma unroll
@@ -309,7 +329,7 @@ __device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState
             const v2 yB = STASH ? stash_load(slot + k * 256) : S.accB[k];
             o[k] = v2fma(mdtdx, v2sub(S.D[k], gam[k]), yB);  // Right of row r-2 = Phi-[r-1] = -Gamma[r-1]
         }
-        if (r - 2 >= W.r0) acc_store(X, r - 2, o);
+        if (EDGE) { if (r - 2 >= W.r0) acc_store(X, r - 2, o); } else acc_store_owned(X, r - 2, o);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             S.D[k] = v2add(v2sub(php[k], S.PhiP[k]), gam[k]);
@@ -336,7 +356,7 @@ __device__ __forceinline__ void acc_read_row(const Ctx &X, int stage, int within
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(u[0][k]), "=f"(u[1][k]) : "r"(a + k * Ctx::PLANE_BYTES));
 }
 
-template <int ORDER, int BC, int LIM, bool WALLTILE, bool STASH, class Ctx>
+template <int ORDER, int BC, int LIM, bool WALLTILE, int STASH, class Ctx>
 __device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, int rlast, int lane)
 {
     AccState<ORDER> S;
@@ -351,7 +371,10 @@ __device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, in
         const int r = rbeg + 4 * box;
         mbar_wait(X.bars + 8u * stage, parity);
         // a box needs the EDGE routine if one of its rows is missing, is a wall row, or completes / follows a wall row
-        const bool edge = (r <= 1 && X.P->lo_wall) || (r + 3 >= nx - 1 && X.P->hi_wall) || (r + 3 > rlast);
+        // ... or if one of the rows it finishes is not stored by this warp / is also stored into a neighbour GPU's halo
+        const int ifirst = r - ORDER;  // rows finished by this box: ifirst .. ifirst + 3
+        const bool edge = (r <= 1 && X.P->lo_wall) || (r + 3 >= nx - 1 && X.P->hi_wall) || (r + 3 > rlast) || (ifirst < W.r0) ||
+                          (ifirst < X.peer_lo_end) || (ifirst + 3 >= X.peer_hi_begin);
         if (edge) {
 #pragma unroll 1
             for (int w = 0; w < 4; w++) {
@@ -378,7 +401,7 @@ __device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, in
 }
 
 // MINB = resident warps per SM the register allocation is capped for (launch bounds); STASH see above.
-template <int ORDER, int BC, int LIM, int MINB, bool STASH>
+template <int ORDER, int BC, int LIM, int MINB, int STASH>
 __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_constant__ Step2DTmaParams T)
 {
     constexpr int R = 4, VEC = 2, HL = 1;
@@ -440,7 +463,10 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
     X.lane_off = (uint32_t)(xs - X.x0 + lane * VEC) * 4u;
     X.ybase = rbeg + 2;
     X.nboxes = (rlast - rbeg) / R + 1;
-    if (STASH) W.stash = ((X.bars + 8u * X.stages + 15u) & ~15u) + 8u * lane;  // host adds 2 KB + 16 to the dynamic smem
+    if (STASH) {  // the host adds 2 KB (level 1) / 4 KB (level 2) + 16 bytes to the dynamic shared memory
+        W.stash = ((X.bars + 8u * X.stages + 15u) & ~15u) + 8u * lane;
+        for (int i = 0; i < (STASH >= 2 ? 16 : 8); i++) stash_store(W.stash + i * 256, v2bc(0.0f));
+    }
     if (lane == 0) {
         for (int s = 0; s < X.stages; s++) mbar_init(X.bars + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");

@@ -37,6 +37,16 @@ def oracle():
     return O
 
 
+# FAST-mode tolerance of the CUDA path: |x - ref| <= tol + tol*|ref| on every primitive field.  3e-5 on the survey's parity
+# configs (BASELINE.md section 2 / SURVEY.md App. A).  The scale behind it is the reference's OWN sensitivity to FMA
+# contraction (the same C built -ffp-contract=fast, as on Graviton, vs the x86 build): <= 5e-6 on those configs, but
+# 1.5e-4 on the non-square 2nd-order fixture this repo added (615 steps, density down to 0.12), so that one gets 6e-4.
+# tests/test_oracle_golden.py::test_fast_tolerance_is_anchored_to_the_reference_sensitivity keeps the table honest:
+# every entry must be >= 2x and <= max(3e-5, 5x) the measured sensitivity.
+FAST_TOL_DEFAULT = 3e-5
+FAST_TOL = {"2d_o2_96x160": 6e-4}
+
+
 def load_golden(case: str):
     z = np.load(os.path.join(GOLDEN_DIR, case + ".npz"))
     return z["u"], z["p"], int(z["steps"])

@@ -10,7 +10,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import ORACLE_IC, bits, load_golden, oracle_cfg_for, problem_from_manifest
+from conftest import FAST_TOL, FAST_TOL_DEFAULT, ORACLE_IC, bits, load_golden, oracle_cfg_for, problem_from_manifest
 
 CASES = ["1d_o1_256", "1d_o1_1024", "2d_o1_64", "2d_o1_96x160", "2d_o1_256", "2d_o2_64", "2d_o2_96x160",
          "1d_o2_slice_1024", "omp_o2_64"]
@@ -89,3 +89,23 @@ def test_threads_do_not_change_bits(oracle):
     cfg4 = O.make_cfg(2, 48, 40, order=2, bc=O.BC_OUTFLOW, nthreads=4)
     u0 = O.cons_from_prim(cfg1, O.init_prim(cfg1, O.IC_FOUR_SHOCK))
     assert np.array_equal(bits(O.run(cfg1, u0, 30)), bits(O.run(cfg4, u0, 30)))
+
+
+@pytest.mark.parametrize("case", ["2d_o1_64", "2d_o1_96x160", "2d_o2_64", "2d_o2_96x160", "omp_o2_64", "1d_o1_1024"])
+def test_fast_tolerance_is_anchored_to_the_reference_sensitivity(case, manifest, oracle):
+    """The FAST-mode tolerance of the CUDA path (conftest.FAST_TOL) is stated against how much the reference's own
+    arithmetic moves when the compiler is allowed to contract a*b+c into FMAs (the default on the Graviton builds the
+    README reports): never tighter than 2x that, never looser than max(3e-5, 5x that)."""
+    O = oracle
+    pb = problem_from_manifest(manifest[case])
+    cfg = oracle_cfg_for(O, pb, nthreads=2)
+    gu, gp, gsteps = load_golden(case)
+    u0 = O.cons_from_prim(cfg, O.init_prim(cfg, ORACLE_IC[pb.ic]))
+    uf = O.run_fma_contracted(cfg, u0, gsteps)
+    if uf is None:
+        pytest.skip("host CPU has no FMA")
+    pf = O.prim_from_cons(cfg, uf).astype(np.float64)
+    sens = float((np.abs(pf - gp) / (1.0 + np.abs(gp.astype(np.float64)))).max())
+    tol = FAST_TOL.get(case, FAST_TOL_DEFAULT)
+    assert tol >= 2.0 * sens, f"{case}: tolerance {tol:g} is tighter than 2x the reference's own FMA sensitivity {sens:.2e}"
+    assert tol <= max(FAST_TOL_DEFAULT, 5.0 * sens), f"{case}: tolerance {tol:g} is looser than 5x the sensitivity {sens:.2e}"
