@@ -16,6 +16,13 @@
  * The reference fixes its sizes with `const` globals and is re-edited per run; here they default to the reference's
  * values and can be overridden without recompiling:  ./base_shll [N]   ./base_shll_2d [NX [NY]]   env SHLL_STEPS=<k>
  * (fixed step count, needed for N >= 2^24 where the float clock stalls), SHLL_MODE=fast, SHLL_SAVE=0/1.
+ *
+ * Additions next to the reference's contract (stdout and results.dat stay byte-identical, everything
+ * below goes to stderr or to its own file):
+ *   SHLL_SAVE_BIN=1          results.bin: the same primitives as results.dat as raw little-endian float32 planes behind a
+ *                            64-byte header -- formatting 268 M lines with fprintf("%e") dwarfs the GPU time at 16384^2
+ *   SHLL_SNAPSHOT_EVERY=k    snapshot_<step>.bin in the same format every k steps (device-side Compute_P_from_U)
+ *   SHLL_MONITOR=1           max CFL number and the sums of the conserved variables at every snapshot and at the end
  */
 #include <math.h>
 #include <stdio.h>
@@ -143,14 +150,57 @@ void Compute_U_from_P(void)
     DT_ON_DY = DT / DY;
 }
 
+/* results.bin / snapshot_<step>.bin: 64-byte header {"SHLLBIN1", dims, nx, ny, ncomp, steps, 9 x int32 zero}, then ncomp
+ * planes of nx*ny little-endian float32 primitives in the reference's index order (rho, u, [v,] T). */
+static void Save_Binary(const char *path, int steps)
+{
+    FILE *f = fopen(path, "wb");
+    if (!f) { perror(path); exit(1); }
+    int32_t hdr[16];
+    memset(hdr, 0, sizeof(hdr));
+    memcpy(hdr, "SHLLBIN1", 8);
+    hdr[2] = DIMS; hdr[3] = NX; hdr[4] = NY; hdr[5] = NCOMP; hdr[6] = steps;
+    int ok = fwrite(hdr, sizeof(hdr), 1, f) == 1;
+    for (int k = 0; k < NCOMP && ok; k++) ok = fwrite(p[k], sizeof(float), (size_t)N, f) == (size_t)N;
+    if (fclose(f) || !ok) { fprintf(stderr, "short write on %s\n", path); exit(1); }
+}
+
+/* Diagnostics only (the reference has neither): they never feed back into DT. */
+static void Monitor(int steps)
+{
+    float cfl = 0.0f;
+    double sums[4];
+    int rc;
+    if ((rc = shll_max_cfl(ctx, &cfl))) die("shll_max_cfl", rc);
+    if ((rc = shll_conserved_sums(ctx, sums))) die("shll_conserved_sums", rc);
+    const double vol = (double)DX * (DIMS == 2 ? (double)DY : 1.0);
+    fprintf(stderr, "monitor step %d: max CFL %.6f  mass %.12e  momentum %.12e", steps, cfl, sums[0] * vol, sums[1] * vol);
+    if (DIMS == 2) fprintf(stderr, " %.12e", sums[2] * vol);
+    fprintf(stderr, "  energy %.12e\n", sums[NCOMP - 1] * vol);
+}
+
 /* Replaces the body of the reference's time loop: NO_STEPS x {Compute_F_from_P; Update_U_from_F; Compute_P_from_U}. */
 void Run_Time_Steps(void)
 {
     int rc;
+    const int every = getenv("SHLL_SNAPSHOT_EVERY") ? atoi(getenv("SHLL_SNAPSHOT_EVERY")) : 0;
+    const int monitor = getenv("SHLL_MONITOR") ? atoi(getenv("SHLL_MONITOR")) : 0;
     if ((rc = shll_upload_u(ctx, (const float *const *)u))) die("shll_upload_u", rc);
-    if ((rc = shll_run(ctx, NO_STEPS))) die("shll_run", rc);
+    if (monitor) Monitor(0);
+    int done = 0;
+    while (every > 0 && done + every < NO_STEPS) {
+        if ((rc = shll_run(ctx, every))) die("shll_run", rc);
+        done += every;
+        if ((rc = shll_download_p(ctx, p, a))) die("shll_download_p", rc);
+        char name[64];
+        snprintf(name, sizeof(name), "snapshot_%08d.bin", done);
+        Save_Binary(name, done);
+        if (monitor) Monitor(done);
+    }
+    if ((rc = shll_run(ctx, NO_STEPS - done))) die("shll_run", rc);
     if ((rc = shll_download_u(ctx, u))) die("shll_download_u", rc);
     if ((rc = shll_download_p(ctx, p, a))) die("shll_download_p", rc); /* the last Compute_P_from_U */
+    if (monitor) Monitor(NO_STEPS);
 }
 
 void Save_Results(void)
@@ -215,6 +265,7 @@ int main(int argc, char **argv)
     printf("Completed in %d steps\n", NO_STEPS);
     int save = getenv("SHLL_SAVE") ? atoi(getenv("SHLL_SAVE")) : SAVE_BY_DEFAULT;
     if (save) Save_Results();
+    if (getenv("SHLL_SAVE_BIN") && atoi(getenv("SHLL_SAVE_BIN"))) Save_Binary("results.bin", NO_STEPS);
 
     shll_destroy(ctx);
     Free_Memory();

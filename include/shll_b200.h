@@ -122,6 +122,12 @@ SHLL_API int shll_run_timed(shll_ctx *ctx, long nsteps, float *ms);
  * max over owned cells of (|u| + a) * dt_on_dx (and the y analogue).  Never feeds back into DT. */
 SHLL_API int shll_max_cfl(shll_ctx *ctx, float *cfl);
 
+/* Diagnostic only: sums over the owned cells of each conserved component -- mass, momentum
+ * (x, and y in 2D), total energy per unit cell volume; sums[k] = 0 for k >= ncomp.  FP64 accumulation in a fixed order
+ * (reproducible run to run).  With reflective walls (base_shll.c:93-110) mass and energy are conserved by the scheme up
+ * to FP32 rounding of the update; multi-GPU callers add the per-slab sums. */
+SHLL_API int shll_conserved_sums(shll_ctx *ctx, double sums[4]);
+
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 SHLL_API long shll_launch_count(const shll_ctx *ctx);
 /* Name of the kernel variant the context selected, for logs. */

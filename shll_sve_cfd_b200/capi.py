@@ -21,6 +21,7 @@ IPC_BYTES = 64
 API_SYMBOLS = [
     "shll_abi_version", "shll_last_error", "shll_count_steps", "shll_create", "shll_destroy", "shll_upload_u",
     "shll_download_u", "shll_download_p", "shll_run", "shll_sync", "shll_run_timed", "shll_max_cfl",
+    "shll_conserved_sums",
     "shll_launch_count", "shll_variant_name", "shll_peer_export", "shll_peer_connect",
 ]
 
@@ -76,6 +77,7 @@ def lib():
         L.shll_sync.argtypes = [C.c_void_p]
         L.shll_run_timed.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_float)]
         L.shll_max_cfl.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.shll_conserved_sums.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.shll_launch_count.restype = C.c_long
         L.shll_launch_count.argtypes = [C.c_void_p]
         L.shll_variant_name.restype = C.c_char_p
@@ -156,6 +158,12 @@ class Solver:
         v = C.c_float(0)
         self._ck(lib().shll_max_cfl(self._h, C.byref(v)))
         return v.value
+
+    def conserved_sums(self) -> np.ndarray:
+        """FP64 sums of the conserved components over the owned cells (mass, momentum, energy): a monitor, like max_cfl."""
+        v = (C.c_double * 4)()
+        self._ck(lib().shll_conserved_sums(self._h, v))
+        return np.array(v[:], dtype=np.float64)
 
     @property
     def launches(self) -> int:

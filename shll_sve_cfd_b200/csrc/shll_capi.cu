@@ -8,6 +8,7 @@
 // There is no host fallback anywhere in this file: every entry point either runs CUDA work or returns an error.
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <vector>
 #include <unistd.h>
 
 #include <cmath>
@@ -47,6 +48,7 @@ struct shll_ctx {
     float *state;         // 2 * ncomp * plane_elems floats
     unsigned *flags;
     float *scratch;       // lazily allocated: primitive download (ncomp + 1 planes of ncells)
+    double *sums_dev;     // lazily allocated: per-block partial sums of shll_conserved_sums
     int cur;              // which ping-pong buffer holds the current state
     bool has_state;
     cudaStream_t stream;
@@ -323,6 +325,7 @@ int shll_destroy(shll_ctx *c)
     }
     if (c->scratch) cudaFree(c->scratch);
     if (c->tmap_dev) cudaFree(c->tmap_dev);
+    if (c->sums_dev) cudaFree(c->sums_dev);
     if (c->graph) cudaGraphExecDestroy(c->graph);
     if (c->strips) cudaFree(c->strips);
     if (c->round_done) cudaFree(c->round_done);
@@ -694,6 +697,28 @@ int shll_max_cfl(shll_ctx *c, float *cfl)
     c->launches++;
     CK(c, cudaMemcpyAsync(cfl, out_dev, sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    return SHLL_OK;
+}
+
+int shll_conserved_sums(shll_ctx *c, double sums[4])
+{
+    if (!c || !sums) return fail(c, SHLL_E_INVAL, "shll_conserved_sums: null argument");
+    if (!c->has_state) return fail(c, SHLL_E_STATE, "shll_conserved_sums before shll_upload_u");
+    CK(c, cudaSetDevice(c->cfg.device));
+    const int nb = conserved_sums_blocks();
+    if (!c->sums_dev) CK(c, cudaMalloc(&c->sums_dev, (size_t)nb * 4 * sizeof(double)));
+    const float *uin[4] = {nullptr, nullptr, nullptr, nullptr};
+    for (int k = 0; k < c->ncomp; k++) uin[k] = c->plane(c->cur, k);
+    CK(c, launch_conserved_sums(c->ncomp, uin, c->ncells, c->sums_dev, c->stream));
+    c->launches++;
+    std::vector<double> host((size_t)nb * 4);
+    CK(c, cudaMemcpyAsync(host.data(), c->sums_dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 4; k++) {
+        double t = 0.0;
+        for (int b = 0; b < nb; b++) t += host[(size_t)b * 4 + k];
+        sums[k] = (k < c->ncomp) ? t : 0.0;
+    }
     return SHLL_OK;
 }
 

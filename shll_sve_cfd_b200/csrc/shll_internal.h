@@ -37,4 +37,8 @@ cudaError_t launch_prim(int dims, int mode, int tform, const float *const u[4], 
 cudaError_t launch_max_cfl(int dims, int mode, int tform, const float *const u[4], long ncells, float dtdx, float dtdy,
                            float *out_dev, cudaStream_t s);
 
+// Per-block FP64 partial sums of the conserved components (conserved_sums_blocks() x 4 doubles), fixed order.
+int conserved_sums_blocks();
+cudaError_t launch_conserved_sums(int ncomp, const float *const u[4], long ncells, double *partial_dev, cudaStream_t s);
+
 }  // namespace shll

@@ -159,4 +159,42 @@ cudaError_t launch_max_cfl(int dims, int mode, int tform, const float *const u[4
     return cudaGetLastError();
 }
 
+// ---------------------------------------------------------------------------------------------- conservation sums
+// Sum of every conserved component over the owned cells (mass, momentum, total energy per unit cell volume): the
+// monitor SURVEY.md section 8(f) asks for next to the CFL number.  FP64 accumulation, fixed summation order (grid-stride
+// per thread, shuffle tree per warp, warp order per block, block order on the host), so the result is reproducible
+// run to run; it never feeds back into the march.
+constexpr int SUM_BLOCKS = 148 * 4, SUM_THREADS = 256;
+
+__global__ void __launch_bounds__(SUM_THREADS) sums_kernel(PlanePtrs P, int ncomp, long n, double *partial)
+{
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (long c = blockIdx.x * (long)blockDim.x + threadIdx.x; c < n; c += (long)gridDim.x * blockDim.x)
+        for (int k = 0; k < ncomp; k++) acc[k] += (double)P.u[k][c];
+    __shared__ double wsum[SUM_THREADS / 32][4];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    for (int k = 0; k < 4; k++) {
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) acc[k] += __shfl_down_sync(0xffffffffu, acc[k], off);
+        if (lane == 0) wsum[w][k] = acc[k];
+    }
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double t = 0.0;
+        for (int i = 0; i < SUM_THREADS / 32; i++) t += wsum[i][threadIdx.x];
+        partial[blockIdx.x * 4 + threadIdx.x] = t;
+    }
+}
+
+int conserved_sums_blocks() { return SUM_BLOCKS; }
+
+cudaError_t launch_conserved_sums(int ncomp, const float *const u[4], long ncells, double *partial_dev, cudaStream_t s)
+{
+    PlanePtrs P;
+    for (int k = 0; k < 4; k++) { P.u[k] = u[k]; P.p[k] = nullptr; }
+    P.a = nullptr;
+    sums_kernel<<<SUM_BLOCKS, SUM_THREADS, 0, s>>>(P, ncomp, ncells, partial_dev);
+    return cudaGetLastError();
+}
+
 }  // namespace shll

@@ -254,8 +254,12 @@ def test_cfl_diagnostic_and_api_state_errors(oracle):
         p, a = programs.prim_from_cons(pb, u0)
         want = float(np.max((np.maximum(np.abs(p[1]), np.abs(p[2])) + a) * np.float32(0.125)))
         assert abs(s.max_cfl() - want) <= 1e-6
+        sums = s.conserved_sums()                          # mass, x / y momentum, energy: FP64, fixed order
+        want_sums = u0.astype(np.float64).sum(axis=1)
+        assert np.allclose(sums, want_sums, rtol=1e-12, atol=1e-9), (sums, want_sums)
+        assert np.array_equal(sums, s.conserved_sums()), "fixed summation order: reproducible"
         before = s.download_u()
-        assert np.array_equal(bits(before), bits(u0))     # the monitor never changes the state or DT
+        assert np.array_equal(bits(before), bits(u0))     # the monitors never change the state or DT
         s.run(0)
         assert np.array_equal(bits(s.download_u()), bits(u0))
 
@@ -275,10 +279,12 @@ def test_4096x4096_conserves_mass_and_keeps_symmetry_properties():
         s.upload_u(u0)
         s.run(40)
         u2 = s.download_u()
+        dev_sums = s.conserved_sums()
     assert np.array_equal(bits(u1), bits(u2)), "same input, same bits"
     m0, m1 = u0[0].astype(np.float64).sum(), u1[0].astype(np.float64).sum()
     e0, e1 = u0[3].astype(np.float64).sum(), u1[3].astype(np.float64).sum()
     assert abs(m1 - m0) / m0 < 1e-6 and abs(e1 - e0) / e0 < 1e-6
+    assert np.allclose(dev_sums, u2.astype(np.float64).sum(axis=1), rtol=1e-12, atol=1e-6)   # device-side monitor, full size
     assert (u1[0] > 0).all() and np.isfinite(u1).all()
 
 

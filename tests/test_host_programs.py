@@ -72,3 +72,35 @@ def test_fixed_step_count_for_grids_whose_float_clock_stalls(tmp_path):
     assert pr.returncode != 0 and "stalls" in pr.stderr     # the reference would loop forever here
     out = _run("2nd_order_base_shll_1d", [1 << 26], tmp_path, env={"SHLL_STEPS": "20", "SHLL_SAVE": "0"})
     assert out == "Completed in 20 steps\n"
+
+
+def _read_bin(path):
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"SHLLBIN1"
+    dims, nx, ny, ncomp, steps = np.frombuffer(raw[8:28], dtype="<i4")
+    planes = np.frombuffer(raw[64:], dtype="<f4").reshape(ncomp, nx * ny)
+    return dict(dims=int(dims), nx=int(nx), ny=int(ny), steps=int(steps)), planes
+
+
+def test_binary_dump_snapshots_and_monitor(manifest, tmp_path):
+    """binary dump, periodic snapshots, CFL / conservation monitor -- none of them may change
+    stdout, results.dat or the result itself."""
+    env = {"SHLL_SAVE": "1", "SHLL_SAVE_BIN": "1", "SHLL_SNAPSHOT_EVERY": "100", "SHLL_MONITOR": "1"}
+    path = os.path.join(HOST, "base_shll_2d")
+    pr = subprocess.run([path, "256"], cwd=tmp_path, env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert pr.returncode == 0, pr.stderr
+    assert pr.stdout == "Completed in 205 steps\nSaving to file\nCompleted saving data\n"
+    assert _md5(os.path.join(tmp_path, "results.dat")) == manifest["2d_o1_256"]["results_dat_md5"]
+    _, gp, _ = load_golden("2d_o1_256")
+    hdr, planes = _read_bin(os.path.join(tmp_path, "results.bin"))
+    assert hdr == dict(dims=2, nx=256, ny=256, steps=205)
+    assert np.array_equal(bits(planes), bits(gp))                      # raw float32: the exact primitives, not 7 digits
+    snaps = sorted(f for f in os.listdir(tmp_path) if f.startswith("snapshot_"))
+    assert snaps == ["snapshot_00000100.bin", "snapshot_00000200.bin"]
+    assert _read_bin(os.path.join(tmp_path, snaps[1]))[0]["steps"] == 200
+    mon = [l for l in pr.stderr.splitlines() if l.startswith("monitor step")]
+    assert [int(l.split()[2].rstrip(":")) for l in mon] == [0, 100, 200, 205]
+    mass = [float(l.split("mass")[1].split()[0]) for l in mon]
+    assert max(mass) - min(mass) < 1e-6 * mass[0]                       # reflective walls conserve mass
+    cfl = [float(l.split("max CFL")[1].split()[0]) for l in mon]
+    assert all(0.1 < c < 0.5 for c in cfl)
