@@ -192,6 +192,8 @@ void plan_2d_fallback(shll_ctx *c)
 void plan_1d(shll_ctx *c)
 {
     c->key.vec = 4;
+    c->key.acc = c->cfg.mode == SHLL_MODE_FAST && c->cfg.order == 2 && env_int("SHLL_ACC", 1) != 0;
+    c->key.acc_cfg = env_int("SHLL_ACC_CFG", 0);
     c->ntiles = (c->cfg.nx + 119) / 120;
     c->nchunks = 1;
 }
@@ -304,7 +306,7 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
             plan_2d_fallback(c);
         }
     }
-    snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? (c->key.acc ? "_tma_acc" : "_tma") : "",
+    snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? (c->key.acc ? "_tma_acc" : "_tma") : ((g.dims == 1 && c->key.acc) ? "_acc" : ""),
              g.order, g.bc == SHLL_BC_REFLECT ? "reflect" : "outflow", g.order == 2 ? (g.limiter == SHLL_LIM_MC ? "mc_" : "minmod_") : "",
              g.mode == SHLL_MODE_STRICT ? "strict" : "fast", c->key.pow2 ? "pow2" : "gendt", c->key.vec, c->ntiles, c->nchunks);
 #undef CKC
@@ -465,10 +467,15 @@ int launch_one_step(shll_ctx *c)
         P.lo_wall = lo_wall; P.hi_wall = hi_wall;
         P.ntiles = c->ntiles;
         P.dtdx = g.dt_on_dx; P.half_dtdx = 0.5f * g.dt_on_dx; P.alpha = g.alpha;
+        P.quarter = 0.25f;
+        // 8 consecutive tiles per warp on large tubes (B200 sweep: profiles/); small tubes keep one warp per tile so that all SMs work
+        P.tiles_per_warp = env_int("SHLL_1D_TILES_PER_WARP", c->ntiles >= 8 * 4096 ? 8 : (c->ntiles >= 4096 ? c->ntiles / 4096 : 1));
+        if (P.tiles_per_warp < 1) P.tiles_per_warp = 1;
         S.edge_warps_lo = 1;
         S.edge_warps_hi = (unsigned)((g.nx - 1) / 120 - (g.nx - g.order) / 120 + 1);
         P.sync = S;
-        dim3 block(256), grid((c->ntiles + 7) / 8);
+        const int warps = (c->ntiles + P.tiles_per_warp - 1) / P.tiles_per_warp;  // a warp marches through consecutive tiles
+        dim3 block(128), grid((warps + 3) / 4);
         e = launch_step1d(c->key, P, grid, block, c->stream);
     }
     if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "step kernel launch failed (%s): %s", c->variant, cudaGetErrorString(e));

@@ -4,6 +4,7 @@
 
 #include "persist1d.cuh"
 #include "step1d.cuh"
+#include "step1d_acc.cuh"
 #include "step2d.cuh"
 #include "step2d_tma.cuh"
 #include "step2d_acc.cuh"
@@ -14,7 +15,7 @@ struct KernelKey {
     int order, bc, lim, mode, vec, tform;
     bool pow2;
     bool tma;  // 2D only: TMA-fed kernel (needs ny % 4 == 0)
-    bool acc;  // 2D FAST, TMA, 2 cells per lane: face-flux accumulate kernel (step2d_acc.cuh)
+    bool acc;  // FAST: face-flux kernels (2D: TMA + 2 cells per lane, step2d_acc.cuh; 1D order 2: step1d_acc.cuh)
     int acc_cfg;  // its register cap / stash variant (step2d_acc.cu)
 };
 

@@ -17,6 +17,15 @@ static cudaError_t go(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3
 template <int ORDER, int BC, int LIM>
 static cudaError_t by_mode(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s)
 {
+    if (k.mode == MODE_FAST && ORDER == 2 && k.acc) {  // face-flux form, packed cell pairs (step1d_acc.cuh)
+        const dim3 g4 = grid, b4 = block;
+        switch (k.acc_cfg) {
+        case 0: step1d_acc_kernel<BC, LIM, 4><<<g4, b4, 0, s>>>(p); break;
+        case 2: step1d_acc_kernel<BC, LIM, 8><<<g4, b4, 0, s>>>(p); break;
+        default: step1d_acc_kernel<BC, LIM, 6><<<g4, b4, 0, s>>>(p); break;
+        }
+        return cudaGetLastError();
+    }
     if (k.mode == MODE_FAST) return go<ORDER, BC, LIM, MODE_FAST, TFORM_2D>(k, p, grid, block, s);  // FAST ignores tform
     if (k.tform == TFORM_1D) return go<ORDER, BC, LIM, MODE_STRICT, TFORM_1D>(k, p, grid, block, s);
     return go<ORDER, BC, LIM, MODE_STRICT, TFORM_2D>(k, p, grid, block, s);

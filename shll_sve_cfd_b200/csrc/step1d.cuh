@@ -8,6 +8,8 @@
 // cell stencil is closed with in-thread neighbours plus one shuffle per plane per direction, and no warp ever
 // talks to another.  Algorithmic traffic: 3 planes read + 3 written = 24 B per cell per step.
 #pragma once
+#include <cstdint>
+
 #include "halo_sync.cuh"
 #include "shll_math.cuh"
 
@@ -24,14 +26,75 @@ struct Step1DParams {
     int lo_wall, hi_wall;
     int ntiles;
     float dtdx, half_dtdx, alpha;
+    int tiles_per_warp;  // step1d_acc.cuh: consecutive tiles one warp marches through (register prefetch of the next one)
+    float quarter;  // 0.25f as a parameter (register operand of the one-LOP3 sign transfer, step1d_acc.cuh)
     HaloSync sync;  // multi-GPU only
 };
+
+// ---- how a warp gets its tiles ------------------------------------------------------------------------------------
+// A warp marches through `tiles_per_warp` consecutive tiles.  Their loads go through a per-warp shared-memory ring filled
+// by cp.async (LDGSTS, 16 bytes per lane per plane, L1 bypassed): STAGES-1 tiles are in flight per warp without holding
+// registers, which is what it takes to cover HBM latency at ~6.5 TB/s with 16-24 resident warps per SM (one tile per warp,
+// or a register prefetch of ONE tile ahead, stalled on the long scoreboard for 6 of every 7 issue cycles and stopped at 77 %
+// of the HBM roofline: profiles/r01_1d_o2_acc_regprefetch.ncu.txt).  Every lane reads back only the 16 bytes it copied itself,
+// so no cross-lane synchronisation is needed.  The address is clamped to the last float4 inside the allocation
+// [-PAD1D, roundup4(n) + PAD1D) (only the ragged last tile needs it).  EDGE tiles -- the only ones that can read halo cells
+// a neighbour GPU has just written -- ignore the ring's copy and load directly after their halo wait.
+constexpr int STEP1D_STAGES = 4;
+
+__device__ __forceinline__ void step1d_prefetch(const Step1DParams &P, int tile, int lane, uint32_t slot)
+{
+    const int jl = min(tile * 120 + (lane - 1) * 4, ((P.n + 3) & ~3));
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + k * 512u), "l"(P.in[k] + jl) : "memory");
+}
+
+// tile_fn(tile, lane, interior, cur[3]); blocks are 128 threads (4 warps); ORDER decides which tiles are interior.
+template <class F>
+__device__ __forceinline__ void step1d_ring_march(const Step1DParams &P, F &&tile_fn, int order)
+{
+    __shared__ __align__(16) float4 ring[4][STEP1D_STAGES][3][32];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    const int w = blockIdx.x * (blockDim.x >> 5) + wib;
+    const int t0 = w * P.tiles_per_warp, t1 = min(t0 + P.tiles_per_warp, P.ntiles);
+    if (t0 >= t1) return;
+    const uint32_t base = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][0][lane]);
+    constexpr uint32_t STAGE_BYTES = 3 * 512;
+#pragma unroll
+    for (int s = 0; s < STEP1D_STAGES - 1; s++) {
+        if (t0 + s < t1) step1d_prefetch(P, t0 + s, lane, base + s * STAGE_BYTES);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
+    int stage = 0;
+    for (int tile = t0; tile < t1; tile++) {
+        {   // refill the stage whose tile was consumed in the previous iteration
+            const int ahead = tile + STEP1D_STAGES - 1;
+            int fill = stage + STEP1D_STAGES - 1;
+            if (fill >= STEP1D_STAGES) fill -= STEP1D_STAGES;
+            if (ahead < t1) step1d_prefetch(P, ahead, lane, base + fill * STAGE_BYTES);
+            asm volatile("cp.async.commit_group;" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group %0;" ::"n"(STEP1D_STAGES - 1) : "memory");
+        float4 cur[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++)
+            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                         : "=f"(cur[k].x), "=f"(cur[k].y), "=f"(cur[k].z), "=f"(cur[k].w)
+                         : "r"(base + stage * STAGE_BYTES + k * 512u)
+                         : "memory");
+        // interior tile: all 128 loaded cells and their +-ORDER neighbours are real owned cells of this slab
+        const bool interior = (tile > 0) && ((long)tile * 120 + 124 + order <= (long)P.n - order);
+        tile_fn(tile, lane, interior, cur);
+        if (++stage == STEP1D_STAGES) stage = 0;
+    }
+}
 
 // One warp tile.  EDGE = false is the interior fast path: no wall selects, no ragged stores, no halo exchange -- the
 // warp-uniform dispatch in step1d_kernel sends only the first tile and the tiles touching the upper end through
 // EDGE = true, so >99.9 % of the warps of a large tube never execute a boundary instruction.
 template <int ORDER, int BC, int LIM, int MODE, int TFORM, bool POW2, bool EDGE>
-__device__ __forceinline__ void step1d_tile(const Step1DParams &P, int tile, int lane)
+__device__ __forceinline__ void step1d_tile(const Step1DParams &P, int tile, int lane, const float4 (&in)[3])
 {
     constexpr int VEC = 4;
     constexpr int USEFUL = 30 * VEC;
@@ -52,7 +115,9 @@ __device__ __forceinline__ void step1d_tile(const Step1DParams &P, int tile, int
     float u[VEC][3], fp[VEC][3], fm[VEC][3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
-        float4 t = *reinterpret_cast<const float4 *>(P.in[k] + jl);  // plain (coherent) load: halo cells are written by a peer GPU
+        float4 t = in[k];
+        // plain (coherent) load AFTER the halo wait above: halo cells are written by a peer GPU while the kernel is resident
+        if (EDGE) t = *reinterpret_cast<const float4 *>(P.in[k] + jl);
         u[0][k] = t.x; u[1][k] = t.y; u[2][k] = t.z; u[3][k] = t.w;
     }
 #pragma unroll
@@ -163,15 +228,12 @@ __device__ __forceinline__ void step1d_tile(const Step1DParams &P, int tile, int
 }
 
 template <int ORDER, int BC, int LIM, int MODE, int TFORM, bool POW2>
-__global__ void __launch_bounds__(256) step1d_kernel(const Step1DParams P)
+__global__ void __launch_bounds__(128) step1d_kernel(const Step1DParams P)
 {
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tile >= P.ntiles) return;
-    // interior tile: all 128 loaded cells and their +-ORDER neighbours are real owned cells of this slab
-    const bool interior = (tile > 0) && ((long)tile * 120 + 124 + ORDER <= (long)P.n - ORDER);
-    if (interior) step1d_tile<ORDER, BC, LIM, MODE, TFORM, POW2, false>(P, tile, lane);
-    else step1d_tile<ORDER, BC, LIM, MODE, TFORM, POW2, true>(P, tile, lane);
+    step1d_ring_march(P, [&](int tile, int lane, bool interior, const float4(&cur)[3]) {
+        if (interior) step1d_tile<ORDER, BC, LIM, MODE, TFORM, POW2, false>(P, tile, lane, cur);
+        else step1d_tile<ORDER, BC, LIM, MODE, TFORM, POW2, true>(P, tile, lane, cur);
+    }, ORDER);
 }
 
 }  // namespace shll

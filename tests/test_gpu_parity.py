@@ -209,15 +209,21 @@ def test_persistent_1d_any_round_length_and_both_modes(K, oracle, monkeypatch):
     u0 = _random_state(pb, seed=K)
     got, ref, _ = _gpu_vs_oracle(pb, oracle, u0, 100)
     assert np.array_equal(bits(got), bits(ref))
-    # FAST mode: persistent and streaming kernels share the per-cell device code -> identical bits
+    # FAST mode: the persistent kernel shares the per-cell device code of the window-form streaming kernel (SHLL_ACC=0) ->
+    # identical bits; the default streaming kernel (face-flux form, step1d_acc.cuh) rounds differently -> tolerance
     with programs.make_solver(pb, capi.MODE_FAST) as s:
         s.upload_u(u0); s.run(100); a = s.download_u(); launches_persist = s.launches
     monkeypatch.setenv("SHLL_PERSIST", "0")
     monkeypatch.setenv("SHLL_GRAPH", "0")
     with programs.make_solver(pb, capi.MODE_FAST) as s:
-        s.upload_u(u0); s.run(100); b = s.download_u(); launches_stream = s.launches
+        s.upload_u(u0); s.run(100); b = s.download_u(); launches_stream = s.launches; name = s.variant
+    assert "_acc_" in name and launches_persist == 1 and launches_stream == 100
+    assert (np.abs(a.astype(np.float64) - b) <= 3e-5 + 3e-5 * np.abs(a)).all(), np.abs(a - b).max()
+    assert (np.abs(b.astype(np.float64) - ref) <= 3e-5 + 3e-5 * np.abs(ref)).all(), np.abs(b - ref).max()
+    monkeypatch.setenv("SHLL_ACC", "0")
+    with programs.make_solver(pb, capi.MODE_FAST) as s:
+        s.upload_u(u0); s.run(100); b = s.download_u()
     assert np.array_equal(bits(a), bits(b))
-    assert launches_persist == 1 and launches_stream == 100
 
 
 def test_cuda_graph_replay_small_grid_matches_single_launches(oracle, monkeypatch):
