@@ -34,6 +34,7 @@ struct Persist1DParams {
     int hmax;             // strip capacity in cells (= K * ORDER)
     long nsteps;
     float dtdx, half_dtdx, alpha;
+    float quarter;        // 0.25f (see step1d_acc.cuh)
     unsigned long long timeout_ns;
 };
 
@@ -122,44 +123,81 @@ __global__ void __launch_bounds__(1024, 1) persist1d_kernel(const Persist1DParam
             __syncthreads();
             const float *lo_w = box + ((warp > 0 ? warp - 1 : 0) * 4) * 6;           // previous warp: slots 2,3 = its lanes 30,31
             const float *hi_w = box + ((warp < nwarps - 1 ? warp + 1 : warp) * 4) * 6;  // next warp: slots 0,1 = its lanes 0,1
+            if constexpr (MODE == MODE_FAST && ORDER == 2) {
+                // FAST 2nd order: face-flux form, operation for operation the arithmetic of step1d_acc.cuh (scalar twins of its
+                // packed instructions), so the persistent and the streaming march give the same bits.
+                const bool edge = at_lo || at_hi;
+                const float q = edge ? 0.0f : P.quarter;  // wall cells are first order
 #pragma unroll
-            for (int k = 0; k < 3; k++) {
-                float fpL = __shfl_up_sync(full, fp[k], 1);    // F+ of cell c-1
-                float fmR = __shfl_down_sync(full, fm[k], 1);  // F- of cell c+1
-                if (lane == 0) fpL = lo_w[3 * 6 + k];
-                if (lane == 31) fmR = hi_w[0 * 6 + 3 + k];
-                float left, right;
-                if (BC == BC_REFLECT) {
-                    left = at_lo ? ((k == 1) ? fm[k] : -fm[k]) : fpL;
-                    right = at_hi ? ((k == 1) ? fp[k] : -fp[k]) : fmR;
-                } else {
-                    left = at_lo ? fp[k] : fpL;
-                    right = at_hi ? fm[k] : fmR;
-                }
-                float v = apply_first<MODE>(u[k], P.dtdx, flux_sum<MODE>(fp[k], fm[k], right, left));
-                if (ORDER == 2) {
-                    float fmL = __shfl_up_sync(full, fm[k], 1);
-                    float fpR = __shfl_down_sync(full, fp[k], 1);
-                    if (lane == 0) fmL = lo_w[3 * 6 + 3 + k];
-                    if (lane == 31) fpR = hi_w[0 * 6 + k];
-                    const bool edge = at_lo || at_hi;
-                    float dfp = edge ? 0.0f : limited_slope<LIM>(fpL, fp[k], fpR, P.alpha);
-                    float dfm = edge ? 0.0f : limited_slope<LIM>(fmL, fm[k], fmR, P.alpha);
-                    float ldf = __shfl_up_sync(full, dfp, 1);    // dF+ of cell c-1
-                    float rdf = __shfl_down_sync(full, dfm, 1);  // dF- of cell c+1
-                    if (lane == 0) {   // slope of the previous warp's lane 31, from its lanes 30, 31 and our lane 0
-                        const bool nb_edge = (c - 1 == 0) || (c - 1 == P.n - 1);
-                        ldf = nb_edge ? 0.0f : limited_slope<LIM>(lo_w[2 * 6 + k], lo_w[3 * 6 + k], fp[k], P.alpha);
+                for (int k = 0; k < 3; k++) {
+                    const float g = -fm[k];  // G = -F-
+                    float fpL = __shfl_up_sync(full, fp[k], 1), gL = __shfl_up_sync(full, g, 1);      // cell c-1
+                    float fpR = __shfl_down_sync(full, fp[k], 1), gR = __shfl_down_sync(full, g, 1);  // cell c+1
+                    if (lane == 0) { fpL = lo_w[3 * 6 + k]; gL = -lo_w[3 * 6 + 3 + k]; }
+                    if (lane == 31) { fpR = hi_w[0 * 6 + k]; gR = -hi_w[0 * 6 + 3 + k]; }
+                    const float dp = fsub(fp[k], fpL), dg = fsub(g, gL);  // backward differences of this cell ...
+                    const float rp = fsub(fpR, fp[k]), rg = fsub(gR, g);  // ... and of cell c+1 (its forward ones)
+                    const float phi = face_flux_plus<LIM>(dp, rp, q, fp[k], P.alpha);
+                    const float gam = face_flux_minus<LIM>(dg, rg, q, g, P.alpha);
+                    float phiL = __shfl_up_sync(full, phi, 1);    // Phi+ of cell c-1
+                    float gamR = __shfl_down_sync(full, gam, 1);  // Gamma of cell c+1
+                    if (lane == 0) {   // face flux of the previous warp's lane 31, from its lanes 30, 31 and our lane 0
+                        const float qn = ((c - 1 == 0) || (c - 1 == P.n - 1)) ? 0.0f : P.quarter;
+                        phiL = face_flux_plus<LIM>(fsub(lo_w[3 * 6 + k], lo_w[2 * 6 + k]), dp, qn, lo_w[3 * 6 + k], P.alpha);
                     }
-                    if (lane == 31) {  // slope of the next warp's lane 0, from our lane 31 and its lanes 0, 1
-                        const bool nb_edge = (c + 1 == 0) || (c + 1 == P.n - 1);
-                        rdf = nb_edge ? 0.0f : limited_slope<LIM>(fm[k], hi_w[0 * 6 + 3 + k], hi_w[1 * 6 + 3 + k], P.alpha);
+                    if (lane == 31) {  // face flux of the next warp's lane 0, from our lane 31 and its lanes 0, 1
+                        const float qn = ((c + 1 == 0) || (c + 1 == P.n - 1)) ? 0.0f : P.quarter;
+                        const float g1 = -hi_w[0 * 6 + 3 + k], g2 = -hi_w[1 * 6 + 3 + k];
+                        gamR = face_flux_minus<LIM>(rg, fsub(g2, g1), qn, g1, P.alpha);
                     }
-                    ldf = at_lo ? 0.0f : ldf;
-                    rdf = at_hi ? 0.0f : rdf;
-                    v = apply_second<MODE, POW2>(v, P.half_dtdx, slope_sum(dfp, dfm, rdf, ldf));
+                    // wall ghosts: reflective (-,+,-) of the cell's own opposite flux (base_shll.c:95-97,108-110), outflow its own flux
+                    const float ghost_lo = (BC == BC_REFLECT) ? ((k == 1) ? -g : g) : fp[k];
+                    const float ghost_hi = (BC == BC_REFLECT) ? ((k == 1) ? -fp[k] : fp[k]) : g;
+                    phiL = at_lo ? ghost_lo : phiL;
+                    gamR = at_hi ? ghost_hi : gamR;
+                    const float v = __fmaf_rn(-P.dtdx, fadd(fsub(phi, phiL), fsub(gam, gamR)), u[k]);
+                    u[k] = in_domain ? v : 1.0f;
                 }
-                u[k] = in_domain ? v : 1.0f;
+            } else {
+#pragma unroll
+                for (int k = 0; k < 3; k++) {
+                    float fpL = __shfl_up_sync(full, fp[k], 1);    // F+ of cell c-1
+                    float fmR = __shfl_down_sync(full, fm[k], 1);  // F- of cell c+1
+                    if (lane == 0) fpL = lo_w[3 * 6 + k];
+                    if (lane == 31) fmR = hi_w[0 * 6 + 3 + k];
+                    float left, right;
+                    if (BC == BC_REFLECT) {
+                        left = at_lo ? ((k == 1) ? fm[k] : -fm[k]) : fpL;
+                        right = at_hi ? ((k == 1) ? fp[k] : -fp[k]) : fmR;
+                    } else {
+                        left = at_lo ? fp[k] : fpL;
+                        right = at_hi ? fm[k] : fmR;
+                    }
+                    float v = apply_first<MODE>(u[k], P.dtdx, flux_sum<MODE>(fp[k], fm[k], right, left));
+                    if (ORDER == 2) {
+                        float fmL = __shfl_up_sync(full, fm[k], 1);
+                        float fpR = __shfl_down_sync(full, fp[k], 1);
+                        if (lane == 0) fmL = lo_w[3 * 6 + 3 + k];
+                        if (lane == 31) fpR = hi_w[0 * 6 + k];
+                        const bool edge = at_lo || at_hi;
+                        float dfp = edge ? 0.0f : limited_slope<LIM>(fpL, fp[k], fpR, P.alpha);
+                        float dfm = edge ? 0.0f : limited_slope<LIM>(fmL, fm[k], fmR, P.alpha);
+                        float ldf = __shfl_up_sync(full, dfp, 1);    // dF+ of cell c-1
+                        float rdf = __shfl_down_sync(full, dfm, 1);  // dF- of cell c+1
+                        if (lane == 0) {   // slope of the previous warp's lane 31, from its lanes 30, 31 and our lane 0
+                            const bool nb_edge = (c - 1 == 0) || (c - 1 == P.n - 1);
+                            ldf = nb_edge ? 0.0f : limited_slope<LIM>(lo_w[2 * 6 + k], lo_w[3 * 6 + k], fp[k], P.alpha);
+                        }
+                        if (lane == 31) {  // slope of the next warp's lane 0, from our lane 31 and its lanes 0, 1
+                            const bool nb_edge = (c + 1 == 0) || (c + 1 == P.n - 1);
+                            rdf = nb_edge ? 0.0f : limited_slope<LIM>(fm[k], hi_w[0 * 6 + 3 + k], hi_w[1 * 6 + 3 + k], P.alpha);
+                        }
+                        ldf = at_lo ? 0.0f : ldf;
+                        rdf = at_hi ? 0.0f : rdf;
+                        v = apply_second<MODE, POW2>(v, P.half_dtdx, slope_sum(dfp, dfm, rdf, ldf));
+                    }
+                    u[k] = in_domain ? v : 1.0f;
+                }
             }
         }
 

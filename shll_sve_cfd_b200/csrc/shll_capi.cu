@@ -468,8 +468,10 @@ int launch_one_step(shll_ctx *c)
         P.ntiles = c->ntiles;
         P.dtdx = g.dt_on_dx; P.half_dtdx = 0.5f * g.dt_on_dx; P.alpha = g.alpha;
         P.quarter = 0.25f;
-        // 8 consecutive tiles per warp on large tubes (B200 sweep: profiles/); small tubes keep one warp per tile so that all SMs work
-        P.tiles_per_warp = env_int("SHLL_1D_TILES_PER_WARP", c->ntiles >= 8 * 4096 ? 8 : (c->ntiles >= 4096 ? c->ntiles / 4096 : 1));
+        // 4 (face-flux kernel: 8) consecutive tiles per warp on large tubes (B200 sweep: profiles/); small tubes keep one warp
+        // per tile so that all SMs work
+        const int tpw_big = c->key.acc ? 8 : 4;
+        P.tiles_per_warp = env_int("SHLL_1D_TILES_PER_WARP", c->ntiles >= tpw_big * 4096 ? tpw_big : (c->ntiles >= 4096 ? c->ntiles / 4096 : 1));
         if (P.tiles_per_warp < 1) P.tiles_per_warp = 1;
         S.edge_warps_lo = 1;
         S.edge_warps_hi = (unsigned)((g.nx - 1) / 120 - (g.nx - g.order) / 120 + 1);
@@ -518,6 +520,7 @@ int run_persistent_1d(shll_ctx *c, long nsteps)
     P.n = g.nx; P.nblocks = c->persist_blocks; P.K = c->persist_K; P.hmax = c->persist_K * g.order;
     P.nsteps = nsteps;
     P.dtdx = g.dt_on_dx; P.half_dtdx = 0.5f * g.dt_on_dx; P.alpha = g.alpha;
+    P.quarter = 0.25f;
     P.timeout_ns = (unsigned long long)env_int("SHLL_HALO_TIMEOUT_MS", 5000) * 1000000ull;
     cudaError_t e = launch_persist1d(c->key, P, c->persist_blocks, c->persist_threads, c->stream);
     if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "persistent 1D launch failed: %s", cudaGetErrorString(e));

@@ -209,8 +209,8 @@ def test_persistent_1d_any_round_length_and_both_modes(K, oracle, monkeypatch):
     u0 = _random_state(pb, seed=K)
     got, ref, _ = _gpu_vs_oracle(pb, oracle, u0, 100)
     assert np.array_equal(bits(got), bits(ref))
-    # FAST mode: the persistent kernel shares the per-cell device code of the window-form streaming kernel (SHLL_ACC=0) ->
-    # identical bits; the default streaming kernel (face-flux form, step1d_acc.cuh) rounds differently -> tolerance
+    # FAST mode: the persistent kernel runs, operation for operation, the arithmetic of the streaming kernel (face-flux form,
+    # step1d_acc.cuh) -> identical bits, and both stay within the FAST tolerance of the oracle
     with programs.make_solver(pb, capi.MODE_FAST) as s:
         s.upload_u(u0); s.run(100); a = s.download_u(); launches_persist = s.launches
     monkeypatch.setenv("SHLL_PERSIST", "0")
@@ -218,11 +218,20 @@ def test_persistent_1d_any_round_length_and_both_modes(K, oracle, monkeypatch):
     with programs.make_solver(pb, capi.MODE_FAST) as s:
         s.upload_u(u0); s.run(100); b = s.download_u(); launches_stream = s.launches; name = s.variant
     assert "_acc_" in name and launches_persist == 1 and launches_stream == 100
-    assert (np.abs(a.astype(np.float64) - b) <= 3e-5 + 3e-5 * np.abs(a)).all(), np.abs(a - b).max()
+    assert np.array_equal(bits(a), bits(b))
     assert (np.abs(b.astype(np.float64) - ref) <= 3e-5 + 3e-5 * np.abs(ref)).all(), np.abs(b - ref).max()
-    monkeypatch.setenv("SHLL_ACC", "0")
+
+
+def test_persistent_and_streaming_fast_kernels_agree_bitwise_with_walls_and_mc(monkeypatch):
+    """Reflective walls + MC limiter through both 1D FAST 2nd-order kernels (persistent: scalar; streaming: packed pairs)."""
+    pb = programs.Problem("x", 1, 20000, order=2, bc=capi.BC_REFLECT, limiter=capi.LIM_MC, tform=capi.TFORM_2D)
+    u0 = _random_state(pb, seed=11)
     with programs.make_solver(pb, capi.MODE_FAST) as s:
-        s.upload_u(u0); s.run(100); b = s.download_u()
+        s.upload_u(u0); s.run(64); a = s.download_u(); assert s.launches == 1
+    monkeypatch.setenv("SHLL_PERSIST", "0")
+    monkeypatch.setenv("SHLL_GRAPH", "0")
+    with programs.make_solver(pb, capi.MODE_FAST) as s:
+        s.upload_u(u0); s.run(64); b = s.download_u(); assert s.launches == 64 and "_acc_" in s.variant
     assert np.array_equal(bits(a), bits(b))
 
 
