@@ -130,9 +130,15 @@ def ref_time_per_step(exe, ncomp, ncells, k1, k2, threads=None):
     return (r2["seconds"] - r1["seconds"]) / (k2 - k1), r1["seconds"], r2["seconds"]
 
 
+def _budget(seconds):
+    """CPU-baseline sample length; SHLL_BENCH_CPU_BUDGET scales it (tests use a small factor)."""
+    return seconds * float(os.environ.get("SHLL_BENCH_CPU_BUDGET", "1.0"))
+
+
 def cpu_reference_rate(workload, budget_s=20.0):
     """The reference's own C program (oracle/_ref, kind 'reference') on one host core, bounded sample."""
     from oracle import oracle as O
+    budget_s = _budget(budget_s)
     w = WORKLOADS[workload]
     exe = w["ref"]
     if not O.ref_available(exe):
@@ -183,16 +189,17 @@ def _replica_times(exe, nrep, cap):
     return float(np.mean(secs))
 
 
-def cpu_all_cores_rate(workload, budget_s=15.0):
+def cpu_all_cores_rate(workload, budget_s=15.0, omp_n=4096):
     """Every host core busy with the reference's code for this workload's scheme (BASELINE.json: 'vs CPU base-c/omp').
 
     2nd-order 2D: the reference's own OpenMP program (base-omp/2nd_order_base_shll.c, MC limiter -- same cost per cell) with
     one thread per core.  The other schemes have no threaded build in the reference: one single-threaded copy of the
     program per core, side by side (1024^2 / 65536-cell builds so that the copies fit in host memory), rates added up."""
     from oracle import oracle as O
+    budget_s = _budget(budget_s)
     cores = host_cores()
     if workload == "2d_o2":
-        exe, n = "ref_omp_o2_4096", 4096
+        exe, n = f"ref_omp_o2_{omp_n}", omp_n
         if not O.ref_available(exe):
             return None
         cells = n * n
@@ -205,7 +212,7 @@ def cpu_all_cores_rate(workload, budget_s=15.0):
             t1, t2 = t(k1), t(k2)
             per = max((t2 - t1) / (k2 - k1), 1e-7)
         return dict(value=cells / per, unit=UNIT, cores=cores, kind="reference",
-                    sample=f"oracle/_ref/{exe} (base-omp source, gcc -fopenmp -O3, {cores} threads, 4096^2) step caps {k1} and {k2}: {t1:.3f}s / {t2:.3f}s")
+                    sample=f"oracle/_ref/{exe} (base-omp source, gcc -fopenmp -O3, {cores} threads, {n}^2) step caps {k1} and {k2}: {t1:.3f}s / {t2:.3f}s")
     exe, cells = {"2d_o1": ("ref_2d_o1_1024", 1024 * 1024), "1d_o1": ("ref_1d_o1_65536", 65536),
                   "1d_o2": ("ref_1d_o2_slice_65536", 65536 * 4), "1d_o2_64k": ("ref_1d_o2_slice_65536", 65536 * 4)}[workload]
     if not O.ref_available(exe):
