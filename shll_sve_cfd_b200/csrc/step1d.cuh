@@ -36,7 +36,7 @@ struct Step1DParams {
 // by cp.async (LDGSTS, 16 bytes per lane per plane, L1 bypassed): STAGES-1 tiles are in flight per warp without holding
 // registers, which is what it takes to cover HBM latency at ~6.5 TB/s with 16-24 resident warps per SM (one tile per warp,
 // or a register prefetch of ONE tile ahead, stalled on the long scoreboard for 6 of every 7 issue cycles and stopped at 77 %
-// of the HBM roofline: profiles/r01_1d_o2_acc_regprefetch.ncu.txt).  Every lane reads back only the 16 bytes it copied itself,
+// of the HBM roofline in this round's ncu capture of that version; the ring version is profiles/r01_1d_o2_acc_fast.ncu.txt).  Every lane reads back only the 16 bytes it copied itself,
 // so no cross-lane synchronisation is needed.  The address is clamped to the last float4 inside the allocation
 // [-PAD1D, roundup4(n) + PAD1D) (only the ragged last tile needs it).  EDGE tiles -- the only ones that can read halo cells
 // a neighbour GPU has just written -- ignore the ring's copy and load directly after their halo wait.
