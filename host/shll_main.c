@@ -17,6 +17,10 @@
  * values and can be overridden without recompiling:  ./base_shll [N]   ./base_shll_2d [NX [NY]]   env SHLL_STEPS=<k>
  * (fixed step count, needed for N >= 2^24 where the float clock stalls), SHLL_MODE=fast, SHLL_SAVE=0/1.
  *
+ * Multi-GPU, still ONE process like the reference programs: SHLL_NGPUS=<n> cuts the domain into n slabs along x, one per
+ * GPU (SHLL_DEVICES=0,1,... picks them; a device may be listed twice), halo rows exchanged by the step kernels over
+ * NVLink (shll_group_* in include/shll_b200.h).  stdout and results.dat are byte-identical whatever n is.
+ *
  * Additions next to the reference's contract (stdout and results.dat stay byte-identical, everything
  * below goes to stderr or to its own file):
  *   SHLL_SAVE_BIN=1          results.bin: the same primitives as results.dat as raw little-endian float32 planes behind a
@@ -80,12 +84,13 @@ static int NO_STEPS = 0;
 static float TOTAL_TIME = DEFAULT_TOTAL_TIME;
 
 static float *p[4], *u[4], *a; /* primitives, conserved variables, sound speed: SoA like p0..p3 / u0..u3 */
-static shll_ctx *ctx;
+static shll_group *grp; /* the whole domain: one slab per GPU (a single slab unless SHLL_NGPUS > 1) */
 
 static void die(const char *what, int rc)
 {
-    const char *msg = ctx ? shll_last_error(ctx) : "";
-    if (!msg || !*msg) msg = shll_last_error(NULL); /* errors raised without a context (shll_create, shll_count_steps) */
+    const char *msg = grp ? shll_group_last_error(grp) : "";
+    if (!msg || !*msg) msg = shll_group_last_error(NULL); /* errors raised without a group (shll_group_create) */
+    if (!msg || !*msg) msg = shll_last_error(NULL);       /* ... or without a context (shll_count_steps) */
     fprintf(stderr, "%s failed (%d): %s\n", what, rc, msg);
     exit(1);
 }
@@ -171,8 +176,8 @@ static void Monitor(int steps)
     float cfl = 0.0f;
     double sums[4];
     int rc;
-    if ((rc = shll_max_cfl(ctx, &cfl))) die("shll_max_cfl", rc);
-    if ((rc = shll_conserved_sums(ctx, sums))) die("shll_conserved_sums", rc);
+    if ((rc = shll_group_max_cfl(grp, &cfl))) die("shll_group_max_cfl", rc);
+    if ((rc = shll_group_conserved_sums(grp, sums))) die("shll_group_conserved_sums", rc);
     const double vol = (double)DX * (DIMS == 2 ? (double)DY : 1.0);
     fprintf(stderr, "monitor step %d: max CFL %.6f  mass %.12e  momentum %.12e", steps, cfl, sums[0] * vol, sums[1] * vol);
     if (DIMS == 2) fprintf(stderr, " %.12e", sums[2] * vol);
@@ -185,21 +190,21 @@ void Run_Time_Steps(void)
     int rc;
     const int every = getenv("SHLL_SNAPSHOT_EVERY") ? atoi(getenv("SHLL_SNAPSHOT_EVERY")) : 0;
     const int monitor = getenv("SHLL_MONITOR") ? atoi(getenv("SHLL_MONITOR")) : 0;
-    if ((rc = shll_upload_u(ctx, (const float *const *)u))) die("shll_upload_u", rc);
+    if ((rc = shll_group_upload_u(grp, (const float *const *)u))) die("shll_group_upload_u", rc);
     if (monitor) Monitor(0);
     int done = 0;
     while (every > 0 && done + every < NO_STEPS) {
-        if ((rc = shll_run(ctx, every))) die("shll_run", rc);
+        if ((rc = shll_group_run(grp, every))) die("shll_group_run", rc);
         done += every;
-        if ((rc = shll_download_p(ctx, p, a))) die("shll_download_p", rc);
+        if ((rc = shll_group_download_p(grp, p, a))) die("shll_group_download_p", rc);
         char name[64];
         snprintf(name, sizeof(name), "snapshot_%08d.bin", done);
         Save_Binary(name, done);
         if (monitor) Monitor(done);
     }
-    if ((rc = shll_run(ctx, NO_STEPS - done))) die("shll_run", rc);
-    if ((rc = shll_download_u(ctx, u))) die("shll_download_u", rc);
-    if ((rc = shll_download_p(ctx, p, a))) die("shll_download_p", rc); /* the last Compute_P_from_U */
+    if ((rc = shll_group_run(grp, NO_STEPS - done))) die("shll_group_run", rc);
+    if ((rc = shll_group_download_u(grp, u))) die("shll_group_download_u", rc);
+    if ((rc = shll_group_download_p(grp, p, a))) die("shll_group_download_p", rc); /* the last Compute_P_from_U */
     if (monitor) Monitor(NO_STEPS);
 }
 
@@ -248,8 +253,17 @@ int main(int argc, char **argv)
     cfg.dt_on_dx = DT_ON_DX; cfg.dt_on_dy = DT_ON_DY;
     cfg.device = getenv("SHLL_DEVICE") ? atoi(getenv("SHLL_DEVICE")) : 0;
     cfg.rank = 0; cfg.nranks = 1;
-    int rc = shll_create(&ctx, &cfg);
-    if (rc) die("shll_create", rc);
+    int ngpus = getenv("SHLL_NGPUS") ? atoi(getenv("SHLL_NGPUS")) : 1;
+    int devices[64], ndevices = 0;
+    if (getenv("SHLL_DEVICES")) { /* e.g. 0,1,2,3 -- one entry per slab */
+        char list[256];
+        snprintf(list, sizeof(list), "%s", getenv("SHLL_DEVICES"));
+        for (char *tok = strtok(list, ","); tok && ndevices < 64; tok = strtok(NULL, ",")) devices[ndevices++] = atoi(tok);
+        if (!getenv("SHLL_NGPUS")) ngpus = ndevices;
+        if (ndevices != ngpus) { fprintf(stderr, "SHLL_DEVICES lists %d devices, SHLL_NGPUS is %d\n", ndevices, ngpus); return 1; }
+    }
+    int rc = shll_group_create(&grp, &cfg, ngpus, ndevices ? devices : NULL);
+    if (rc) die("shll_group_create", rc);
 
     /* Take some timesteps: the float clock decides how many (base_shll.c:208-218) */
     if (getenv("SHLL_STEPS")) {
@@ -267,7 +281,7 @@ int main(int argc, char **argv)
     if (save) Save_Results();
     if (getenv("SHLL_SAVE_BIN") && atoi(getenv("SHLL_SAVE_BIN"))) Save_Binary("results.bin", NO_STEPS);
 
-    shll_destroy(ctx);
+    shll_group_destroy(grp);
     Free_Memory();
     return 0;
 }

@@ -154,6 +154,38 @@ SHLL_API int shll_peer_export(shll_ctx *ctx, shll_peer_desc *desc);
 /* side: -1 = lower neighbour (rank-1), +1 = upper neighbour (rank+1). */
 SHLL_API int shll_peer_connect(shll_ctx *ctx, int side, const shll_peer_desc *desc);
 
+/* ---- single-process multi-GPU: a group of slabs behind one handle ------------------------------------
+ * What a C program needs to stay ONE process, as the reference programs are (base-c/base_shll_2d.c:343-371), and still
+ * use every GPU of the box.  `cfg` describes the WHOLE domain (cfg->nx = all rows / cells along x; rank, nranks and --
+ * unless ngpus == 1 -- device are ignored).  Slab r of ngpus owns x indices [r*nx/ngpus, (r+1)*nx/ngpus) on devices[r]
+ * (devices == NULL: device r).  The same device may be listed more than once (slabs then share it; used by the
+ * single-GPU tests of this path).  The group creates one context per slab, connects neighbours with
+ * shll_peer_export / shll_peer_connect (same process => plain peer pointers over NVLink) and feeds every slab from its
+ * own short-lived host thread per call.  Host arrays passed to the group calls are the GLOBAL SoA arrays of the
+ * reference (u0..u3 / p0..p3 of nx*ny floats): each slab copies its own contiguous row block, nothing is staged.
+ * Results are bitwise independent of ngpus in both arithmetic modes (tests/test_group.py, tests/test_multi_gpu.py). */
+typedef struct shll_group shll_group;
+
+SHLL_API int shll_group_create(shll_group **out, const shll_config *cfg, int ngpus, const int *devices);
+SHLL_API int shll_group_destroy(shll_group *g);
+/* Message of the last error on this group (g == NULL: last error of a failed shll_group_create on this thread). */
+SHLL_API const char *shll_group_last_error(const shll_group *g);
+SHLL_API int shll_group_size(const shll_group *g);
+/* The context of one slab (owned by the group), e.g. for shll_variant_name; NULL if out of range. */
+SHLL_API shll_ctx *shll_group_ctx(const shll_group *g, int slab);
+
+SHLL_API int shll_group_upload_u(shll_group *g, const float *const u[4]);
+SHLL_API int shll_group_download_u(shll_group *g, float *const u[4]);
+SHLL_API int shll_group_download_p(shll_group *g, float *const p[4], float *a);
+/* nsteps fused time steps on every slab; returns when all slabs have finished them. */
+SHLL_API int shll_group_run(shll_group *g, long nsteps);
+/* Same, *ms = device time (CUDA events on each slab's stream) of the slowest slab. */
+SHLL_API int shll_group_run_timed(shll_group *g, long nsteps, float *ms);
+/* Diagnostics over the whole domain: max over slabs / sum over slabs in slab order. */
+SHLL_API int shll_group_max_cfl(shll_group *g, float *cfl);
+SHLL_API int shll_group_conserved_sums(shll_group *g, double sums[4]);
+SHLL_API long shll_group_launch_count(const shll_group *g);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,6 +23,9 @@ API_SYMBOLS = [
     "shll_download_u", "shll_download_p", "shll_run", "shll_sync", "shll_run_timed", "shll_max_cfl",
     "shll_conserved_sums",
     "shll_launch_count", "shll_variant_name", "shll_peer_export", "shll_peer_connect",
+    "shll_group_create", "shll_group_destroy", "shll_group_last_error", "shll_group_size", "shll_group_ctx",
+    "shll_group_upload_u", "shll_group_download_u", "shll_group_download_p", "shll_group_run", "shll_group_run_timed",
+    "shll_group_max_cfl", "shll_group_conserved_sums", "shll_group_launch_count",
 ]
 
 
@@ -84,6 +87,22 @@ def lib():
         L.shll_variant_name.argtypes = [C.c_void_p]
         L.shll_peer_export.argtypes = [C.c_void_p, C.POINTER(PeerDesc)]
         L.shll_peer_connect.argtypes = [C.c_void_p, C.c_int, C.POINTER(PeerDesc)]
+        L.shll_group_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config), C.c_int, C.POINTER(C.c_int)]
+        L.shll_group_destroy.argtypes = [C.c_void_p]
+        L.shll_group_last_error.restype = C.c_char_p
+        L.shll_group_last_error.argtypes = [C.c_void_p]
+        L.shll_group_size.argtypes = [C.c_void_p]
+        L.shll_group_ctx.restype = C.c_void_p
+        L.shll_group_ctx.argtypes = [C.c_void_p, C.c_int]
+        L.shll_group_upload_u.argtypes = [C.c_void_p, VPP]
+        L.shll_group_download_u.argtypes = [C.c_void_p, VPP]
+        L.shll_group_download_p.argtypes = [C.c_void_p, VPP, C.c_void_p]
+        L.shll_group_run.argtypes = [C.c_void_p, C.c_long]
+        L.shll_group_run_timed.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_float)]
+        L.shll_group_max_cfl.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        L.shll_group_conserved_sums.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.shll_group_launch_count.restype = C.c_long
+        L.shll_group_launch_count.argtypes = [C.c_void_p]
         _lib = L
     return _lib
 
@@ -185,6 +204,99 @@ class Solver:
     def close(self):
         if self._h:
             lib().shll_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Group:
+    """Single-process multi-GPU: the whole domain behind one handle (shll_group_*), slabs along x on `devices`.
+
+    Arrays are the GLOBAL SoA arrays (ncomp, nx*ny); `devices` may repeat a device (slabs then share it)."""
+
+    def __init__(self, dims, nx, ny=1, ngpus=1, devices=None, order=1, bc=BC_REFLECT, limiter=LIM_MINMOD, tform=TFORM_AUTO,
+                 mode=MODE_STRICT, alpha=1.25, dt_on_dx=0.125, dt_on_dy=0.125, variant=0):
+        self.cfg = Config()
+        self.cfg.struct_size = C.sizeof(Config)
+        self.cfg.dims, self.cfg.nx, self.cfg.ny = dims, nx, (ny if dims == 2 else 1)
+        self.cfg.order, self.cfg.bc, self.cfg.limiter, self.cfg.tform, self.cfg.mode = order, bc, limiter, tform, mode
+        self.cfg.alpha, self.cfg.dt_on_dx, self.cfg.dt_on_dy = alpha, dt_on_dx, dt_on_dy
+        self.cfg.device, self.cfg.rank, self.cfg.nranks, self.cfg.variant = 0, 0, 1, variant
+        self.ncomp = 3 if dims == 1 else 4
+        self.ncells = nx * (ny if dims == 2 else 1)
+        self._h = C.c_void_p(None)
+        dev = None
+        if devices is not None:
+            if len(devices) != ngpus:
+                raise ValueError("len(devices) != ngpus")
+            dev = (C.c_int * ngpus)(*devices)
+        rc = lib().shll_group_create(C.byref(self._h), C.byref(self.cfg), int(ngpus), dev)
+        if rc:
+            raise ShllError(rc, lib().shll_group_last_error(None).decode())
+
+    def _ck(self, rc):
+        if rc:
+            raise ShllError(rc, lib().shll_group_last_error(self._h).decode())
+
+    def upload_u(self, u: np.ndarray):
+        u = np.ascontiguousarray(u, dtype=np.float32)
+        assert u.shape == (self.ncomp, self.ncells), (u.shape, self.ncomp, self.ncells)
+        self._ck(lib().shll_group_upload_u(self._h, _ptrs(u)))
+
+    def download_u(self, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.ncomp, self.ncells), np.float32)
+        self._ck(lib().shll_group_download_u(self._h, _ptrs(out)))
+        return out
+
+    def download_p(self, want_a=False):
+        p = np.empty((self.ncomp, self.ncells), np.float32)
+        a = np.empty(self.ncells, np.float32) if want_a else None
+        self._ck(lib().shll_group_download_p(self._h, _ptrs(p), a.ctypes.data if want_a else None))
+        return (p, a) if want_a else p
+
+    def run(self, nsteps: int):
+        self._ck(lib().shll_group_run(self._h, int(nsteps)))
+
+    def run_timed(self, nsteps: int) -> float:
+        ms = C.c_float(0)
+        self._ck(lib().shll_group_run_timed(self._h, int(nsteps), C.byref(ms)))
+        return ms.value
+
+    def max_cfl(self) -> float:
+        v = C.c_float(0)
+        self._ck(lib().shll_group_max_cfl(self._h, C.byref(v)))
+        return v.value
+
+    def conserved_sums(self) -> np.ndarray:
+        v = (C.c_double * 4)()
+        self._ck(lib().shll_group_conserved_sums(self._h, v))
+        return np.array(v[:], dtype=np.float64)
+
+    @property
+    def size(self) -> int:
+        return lib().shll_group_size(self._h)
+
+    @property
+    def launches(self) -> int:
+        return lib().shll_group_launch_count(self._h)
+
+    def variant(self, slab: int = 0) -> str:
+        return lib().shll_variant_name(lib().shll_group_ctx(self._h, slab)).decode()
+
+    def close(self):
+        if self._h:
+            lib().shll_group_destroy(self._h)
             self._h = C.c_void_p(None)
 
     def __enter__(self):
