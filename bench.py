@@ -3,6 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload W] [--mode strict|fast]
     python bench.py --impl reference ...          # the reference's own C program on the host cores
+    python bench.py --gpus N ...  (no torchrun)   # N GPUs from ONE process through shll_group_* (the C drop-in's shape)
 
 A "step" is one time step of the fused kernel over the whole grid (one launch per GPU).  Workloads (BASELINE.json):
 
@@ -272,6 +273,81 @@ def run_reference_arm(args):
     return 0
 
 
+def run_group_arm(args):
+    """`python bench.py --gpus N` WITHOUT torchrun: the same workload through the single-process multi-GPU front end of the C
+    ABI (shll_group_*: one slab per GPU behind one handle, one host thread per slab), the shape a C drop-in of the reference
+    program has.  Same JSON keys; timing = CUDA events on every slab's stream, the slowest slab counts."""
+    import torch
+    from dataclasses import replace
+    from shll_sve_cfd_b200 import capi, programs
+    w = WORKLOADS[args.workload]
+    n = args.gpus
+    base = programs.PROGRAMS[w["prog"]]
+    nx_per = args.nx or w["nx"]
+    ny = (args.ny or w["ny"]) if base.dims == 2 else 1
+    nx_global = nx_per * n if w["scaling"] == "weak" else nx_per
+    pb = base.resized(nx_global, ny) if base.dims == 2 else base.resized(nx_global)
+    if base.dims == 2:
+        pb = replace(pb, lx=float(nx_global) / float(ny), ly=1.0)
+    _, _, _, dtdx, dtdy = programs.time_constants(pb)
+    K, W = args.steps, args.warmup
+    total_cells = nx_global * ny
+    host_in = torch.empty((pb.ncomp, total_cells), dtype=torch.float32, pin_memory=True)
+    host_out = torch.empty((pb.ncomp, total_cells), dtype=torch.float32, pin_memory=True)
+    host_in.numpy()[...] = programs.cons_from_prim(pb, programs.initial_primitives(pb))
+    out = {}
+    for mode_name in ([args.mode] if args.no_other_mode else [args.mode, "strict" if args.mode == "fast" else "fast"]):
+        mode = capi.MODE_STRICT if mode_name == "strict" else capi.MODE_FAST
+        g = capi.Group(pb.dims, pb.nx, pb.ny, ngpus=n, order=pb.order, bc=pb.bc, limiter=pb.limiter, tform=pb.tform, mode=mode,
+                       alpha=pb.alpha, dt_on_dx=float(dtdx), dt_on_dy=float(dtdy))
+        g.upload_u(host_in.numpy())
+        g.run(W)
+        l0 = g.launches
+        sampler = ClockSampler(0)
+        if mode_name == args.mode:
+            sampler.start(); sampler.wait_first()
+        t0 = time.perf_counter()
+        ms = g.run_timed(K)
+        t1 = time.perf_counter()
+        r = {"ms": ms, "launches": g.launches - l0, "kernel": g.variant(0)}
+        if mode_name == args.mode:
+            sampler.stop()
+            r["clocks"] = sampler.window(t0, t1)
+            if not args.no_e2e:
+                t0 = time.perf_counter()
+                g.upload_u(host_in.numpy()); g.run(K); g.download_u(host_out.numpy())
+                r["e2e_s"] = time.perf_counter() - t0
+        g.close()
+        out[mode_name] = r
+    r = out[args.mode]
+    peak, peak_src = measured_peak_gbs()
+    nloc = total_cells // n
+    achieved = w["bpc"] * nloc / (r["ms"] * 1e-3 / K) / 1e9
+    line = {
+        "metric": METRIC, "value": total_cells * K / (r["ms"] * 1e-3), "unit": UNIT, "n_gpus": n, "steps": K, "warmup": W,
+        "ms_per_step": r["ms"] / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "description": w["desc"], "grid_global": [nx_global, ny], "kernel": r["kernel"],
+                   "arith_mode": args.mode, "parallelism": f"slab{n}, one process (shll_group_*), one host thread per GPU",
+                   "l2": "inputs larger than L2 (no flush needed)" if pb.ncomp * nloc * 4 > L2_BYTES else "state fits in L2"},
+        "gpu_launches": r["launches"],
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "algorithmic_bytes_per_launch": w["bpc"] * nloc, "kernel": r["kernel"], "per": "GPU"},
+        "clocks": r.get("clocks"),
+    }
+    if "e2e_s" in r:
+        nbytes = pb.ncomp * total_cells * 4
+        line["e2e"] = {"value": total_cells * K / r["e2e_s"], "unit": UNIT, "h2d_bytes_per_step": nbytes / K, "d2h_bytes_per_step": nbytes / K,
+                       "seconds": r["e2e_s"], "note": "one shll_group_upload_u (pinned host) + K steps + one shll_group_download_u"}
+    others = [m for m in out if m != args.mode]
+    if others:
+        o = out[others[0]]
+        line["other_mode"] = {"arith_mode": others[0], "kernel": o["kernel"], "value": total_cells * K / (o["ms"] * 1e-3), "unit": UNIT,
+                              "ms_per_step": o["ms"] / K}
+    print(json.dumps(line))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -304,6 +380,8 @@ def main():
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device; the product path has no CPU fallback", file=sys.stderr)
         return 2
+    if world == 1 and args.gpus > 1:   # no torchrun: one process drives all the GPUs through shll_group_*
+        return run_group_arm(args)
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
