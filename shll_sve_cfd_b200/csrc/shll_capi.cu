@@ -62,6 +62,7 @@ struct shll_ctx {
     CUtensorMap *tmap_dev; // the same two descriptors in device memory
     cudaGraphExec_t graph; // single-GPU small grids: GRAPH_STEPS consecutive steps captured once (launch-bound regime)
     bool graph_tried;
+    bool capturing;        // launch_one_step is being recorded into the graph
     int graph_cur;         // ping-pong orientation the graph was captured with
     // persistent 1D march (persist1d.cuh)
     float *strips;
@@ -137,6 +138,18 @@ void plan_2d(shll_ctx *c)
     const int useful = (32 - 2 * hl) * vec;
     c->ntiles = (g.ny + useful - 1) / useful;
     int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? (g.order == 1 ? (c->key.acc ? 18 : 24) : 64) : 64);  // B200 sweeps (profiles/)
+    if (c->key.tma && env_int("SHLL_ROWS_PER_CHUNK", 0) <= 0) {
+        // Small and medium grids: the tuned chunk height leaves most of the GPU without a warp (256^2, 2nd order: 20 one-warp
+        // blocks for 148 SMs).  Shrink the chunks, a TMA box of rows at a time, until about half of the resident warp slots
+        // have an item -- thinner chunks recompute more halo rows, which only matters once the GPU is full
+        // (profiles/r01_sweep_chunk_height_small_grids.log: 256^2 order 2 37.9 -> 9.4 us per step, 1024^2 order 2 42.6 -> 20.3).
+        const int box_rows = (g.order == 1 && !c->key.acc) ? 3 : 4;
+        const int lowest = c->key.acc ? (g.order == 1 ? 2 : 4) : box_rows;
+        int sms = 148;
+        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device) != cudaSuccess || sms < 1) { (void)cudaGetLastError(); sms = 148; }
+        const long want = (long)sms * (g.order == 1 ? 16 : 12) / 2;
+        while (rpc - box_rows >= lowest && (long)c->ntiles * ((g.nx + rpc - 1) / rpc) < want) rpc -= box_rows;
+    }
     if (rpc < 2) rpc = 2;
     int nchunks = (g.nx + rpc - 1) / rpc;
     if (nchunks < 1) nchunks = 1;
@@ -443,6 +456,8 @@ int launch_one_step(shll_ctx *c)
             T.tmap = c->tmap[in];
             T.tmap_global = c->tmap_dev ? c->tmap_dev + in : nullptr;
             T.stages = c->tma_stages;
+            // consecutive steps of a single-GPU run overlap their launch with the predecessor's tail (step2d_acc.cu)
+            T.pdl = (c->key.acc && !multi(c) && (!c->capturing || env_int("SHLL_PDL_GRAPH", 0) != 0) && env_int("SHLL_PDL", 1) != 0) ? 1 : 0;
             dim3 grid(warps);
             if (c->key.acc) e = launch_step2d_acc(c->key, T, grid, c->tma_smem, c->stream);
             else if (g.order == 1) e = launch_step2d_tma_o1(c->key, T, grid, c->tma_smem, c->stream);
@@ -643,7 +658,9 @@ int shll_run(shll_ctx *c, long nsteps)
         const long l0 = c->launches;
         if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int crc = SHLL_OK;
+            c->capturing = true;
             for (int s = 0; s < GRAPH_STEPS && crc == SHLL_OK; s++) crc = launch_one_step(c);
+            c->capturing = false;
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             if (crc == SHLL_OK && e == cudaSuccess && g) {
                 if (cudaGraphInstantiate(&c->graph, g, 0) != cudaSuccess) c->graph = nullptr;

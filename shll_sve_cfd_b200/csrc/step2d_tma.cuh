@@ -30,6 +30,7 @@ struct Step2DTmaParams {
     CUtensorMap tmap;     // INPUT buffer as a 3D tensor {ny, nx+4, 4 planes}, origin = halo row -2 of plane 0
     const CUtensorMap *tmap_global;  // optional copy of the same descriptor in device memory (debug switch SHLL_TMAP_GLOBAL)
     int stages;
+    int pdl;              // step2d_acc: launched with programmatic stream serialization (the kernel then waits for its predecessor itself)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
