@@ -90,4 +90,16 @@ __device__ __forceinline__ void halo_arrive(const HaloSync &S, unsigned *cnt, un
     }
 }
 
+// Programmatic dependent launch (single-GPU step kernels).  A kernel launched with launch_pdl(..., pdl = true) may be placed
+// on the SMs while its predecessor in the stream is still running; it must call this before it touches the state: it lets
+// ITS successor be placed as soon as every block of this grid has started, then waits until the predecessor has completed
+// and its stores are visible.  Everything before the call may only touch registers and shared memory.
+__device__ __forceinline__ void pdl_wait_for_previous_step(int pdl)
+{
+    if (pdl) {
+        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+}
+
 }  // namespace shll

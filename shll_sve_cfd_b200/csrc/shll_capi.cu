@@ -409,6 +409,12 @@ int check_connected(shll_ctx *c)
     return SHLL_OK;
 }
 
+// Programmatic dependent launch of the step kernels (halo_sync.cuh): single GPU, outside stream capture.
+int use_pdl(const shll_ctx *c)
+{
+    return (!multi(c) && (!c->capturing || env_int("SHLL_PDL_GRAPH", 0) != 0) && env_int("SHLL_PDL", 1) != 0) ? 1 : 0;
+}
+
 int launch_one_step(shll_ctx *c)
 {
     const shll_config &g = c->cfg;
@@ -457,7 +463,7 @@ int launch_one_step(shll_ctx *c)
             T.tmap_global = c->tmap_dev ? c->tmap_dev + in : nullptr;
             T.stages = c->tma_stages;
             // consecutive steps of a single-GPU run overlap their launch with the predecessor's tail (step2d_acc.cu)
-            T.pdl = (c->key.acc && !multi(c) && (!c->capturing || env_int("SHLL_PDL_GRAPH", 0) != 0) && env_int("SHLL_PDL", 1) != 0) ? 1 : 0;
+            T.pdl = use_pdl(c);
             dim3 grid(warps);
             if (c->key.acc) e = launch_step2d_acc(c->key, T, grid, c->tma_smem, c->stream);
             else if (g.order == 1) e = launch_step2d_tma_o1(c->key, T, grid, c->tma_smem, c->stream);
@@ -491,6 +497,7 @@ int launch_one_step(shll_ctx *c)
         S.edge_warps_lo = 1;
         S.edge_warps_hi = (unsigned)((g.nx - 1) / 120 - (g.nx - g.order) / 120 + 1);
         P.sync = S;
+        P.pdl = use_pdl(c);
         const int warps = (c->ntiles + P.tiles_per_warp - 1) / P.tiles_per_warp;  // a warp marches through consecutive tiles
         dim3 block(128), grid((warps + 3) / 4);
         e = launch_step1d(c->key, P, grid, block, c->stream);

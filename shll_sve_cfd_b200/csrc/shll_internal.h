@@ -19,6 +19,24 @@ struct KernelKey {
     int acc_cfg;  // its register cap / stash variant (step2d_acc.cu)
 };
 
+// <<<grid, block, smem, s>>> with or without the programmatic-stream-serialization attribute (halo_sync.cuh:
+// pdl_wait_for_previous_step): the launch latency and the block dispatch of step n+1 overlap the tail of step n.
+template <class Params>
+inline cudaError_t launch_pdl(void (*kernel)(Params), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, const Params &p)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 // Each returns cudaSuccess / the launch error; cudaErrorInvalidValue for a combination that was not instantiated.
 cudaError_t launch_step2d_o1(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);
 cudaError_t launch_step2d_o2_strict(const KernelKey &k, const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t s);

@@ -8,10 +8,8 @@ template <int ORDER, int BC, int LIM, int MODE, int TFORM>
 static cudaError_t go(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s)
 {
     if (MODE == MODE_STRICT && ORDER == 2 && !k.pow2)
-        step1d_kernel<ORDER, BC, LIM, MODE, TFORM, false><<<grid, block, 0, s>>>(p);
-    else
-        step1d_kernel<ORDER, BC, LIM, MODE, TFORM, true><<<grid, block, 0, s>>>(p);
-    return cudaGetLastError();
+        return launch_pdl(step1d_kernel<ORDER, BC, LIM, MODE, TFORM, false>, grid, block, 0, s, p.pdl != 0, p);
+    return launch_pdl(step1d_kernel<ORDER, BC, LIM, MODE, TFORM, true>, grid, block, 0, s, p.pdl != 0, p);
 }
 
 template <int ORDER, int BC, int LIM>
@@ -20,11 +18,10 @@ static cudaError_t by_mode(const KernelKey &k, const Step1DParams &p, dim3 grid,
     if (k.mode == MODE_FAST && ORDER == 2 && k.acc) {  // face-flux form, packed cell pairs (step1d_acc.cuh)
         const dim3 g4 = grid, b4 = block;
         switch (k.acc_cfg) {
-        case 0: step1d_acc_kernel<BC, LIM, 4><<<g4, b4, 0, s>>>(p); break;
-        case 2: step1d_acc_kernel<BC, LIM, 8><<<g4, b4, 0, s>>>(p); break;
-        default: step1d_acc_kernel<BC, LIM, 6><<<g4, b4, 0, s>>>(p); break;
+        case 0: return launch_pdl(step1d_acc_kernel<BC, LIM, 4>, g4, b4, 0, s, p.pdl != 0, p);
+        case 2: return launch_pdl(step1d_acc_kernel<BC, LIM, 8>, g4, b4, 0, s, p.pdl != 0, p);
+        default: return launch_pdl(step1d_acc_kernel<BC, LIM, 6>, g4, b4, 0, s, p.pdl != 0, p);
         }
-        return cudaGetLastError();
     }
     if (k.mode == MODE_FAST) return go<ORDER, BC, LIM, MODE_FAST, TFORM_2D>(k, p, grid, block, s);  // FAST ignores tform
     if (k.tform == TFORM_1D) return go<ORDER, BC, LIM, MODE_STRICT, TFORM_1D>(k, p, grid, block, s);

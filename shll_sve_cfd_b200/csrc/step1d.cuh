@@ -28,6 +28,7 @@ struct Step1DParams {
     float dtdx, half_dtdx, alpha;
     int tiles_per_warp;  // step1d_acc.cuh: consecutive tiles one warp marches through (register prefetch of the next one)
     float quarter;  // 0.25f as a parameter (register operand of the one-LOP3 sign transfer, step1d_acc.cuh)
+    int pdl;        // launched with programmatic stream serialization (halo_sync.cuh: pdl_wait_for_previous_step)
     HaloSync sync;  // multi-GPU only
 };
 
@@ -58,6 +59,7 @@ __device__ __forceinline__ void step1d_ring_march(const Step1DParams &P, F &&til
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int w = blockIdx.x * (blockDim.x >> 5) + wib;
     const int t0 = w * P.tiles_per_warp, t1 = min(t0 + P.tiles_per_warp, P.ntiles);
+    pdl_wait_for_previous_step(P.pdl);
     if (t0 >= t1) return;
     const uint32_t base = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][0][lane]);
     constexpr uint32_t STAGE_BYTES = 3 * 512;

@@ -1,6 +1,4 @@
 // step2d_acc.cu -- instantiations of the FAST-mode face-flux accumulate kernel (step2d_acc.cuh): both orders.
-#include <cstring>
-
 #include "shll_internal.h"
 
 namespace shll {
@@ -8,25 +6,7 @@ namespace shll {
 template <int ORDER, int BC, int LIM, int MINB, int STASH>
 static cudaError_t go(const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
 {
-    // Programmatic dependent launch: the blocks of step n+1 are placed on the SMs while the tail of step n drains and sit in
-    // griddepcontrol.wait (step2d_acc.cuh) until step n has completed and flushed -- the launch latency and the block
-    // dispatch of a fresh grid leave the critical path.  p.pdl == 0 (stream capture, SHLL_PDL=0): plain launch.
-    if (p.pdl) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = grid;
-        cfg.blockDim = dim3(32);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = s;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, step2d_acc_kernel<ORDER, BC, LIM, MINB, STASH>, p);
-    }
-    step2d_acc_kernel<ORDER, BC, LIM, MINB, STASH><<<grid, 32, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(step2d_acc_kernel<ORDER, BC, LIM, MINB, STASH>, grid, dim3(32), smem, s, p.pdl != 0, p);
 }
 
 // order 2: register cap (resident warps per SM) / stash level chosen by the host, KernelKey::acc_cfg

@@ -441,13 +441,7 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (T.pdl) {
-        // Launched while the previous step may still be running (programmatic dependent launch): everything above only
-        // touched registers and shared memory.  Let the step after this one be placed as soon as every block of this one
-        // has started, then wait until the previous step has completed and its stores are visible.
-        asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-        asm volatile("griddepcontrol.wait;" ::: "memory");
-    }
+    pdl_wait_for_previous_step(T.pdl);  // everything above only touched registers and shared memory
     if (lane == 0) {
         for (int b = 0; b < X.stages && b < X.nboxes; b++) X.arm(b, b);
     }

@@ -12,8 +12,7 @@ static cudaError_t go(const Step2DParams &p, dim3 grid, dim3 block, cudaStream_t
 template <int BC, int MODE, int VEC>
 static cudaError_t go_tma(const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
 {
-    step2d_tma_kernel<1, BC, LIM_MINMOD, MODE, VEC, true><<<grid, 32, smem, s>>>(p);
-    return cudaGetLastError();
+    return launch_pdl(step2d_tma_kernel<1, BC, LIM_MINMOD, MODE, VEC, true>, grid, dim3(32), smem, s, p.pdl != 0, p);
 }
 
 template <int BC, int MODE>

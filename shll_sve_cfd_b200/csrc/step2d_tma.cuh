@@ -30,7 +30,7 @@ struct Step2DTmaParams {
     CUtensorMap tmap;     // INPUT buffer as a 3D tensor {ny, nx+4, 4 planes}, origin = halo row -2 of plane 0
     const CUtensorMap *tmap_global;  // optional copy of the same descriptor in device memory (debug switch SHLL_TMAP_GLOBAL)
     int stages;
-    int pdl;              // step2d_acc: launched with programmatic stream serialization (the kernel then waits for its predecessor itself)
+    int pdl;              // launched with programmatic stream serialization: the kernel waits for its predecessor itself (halo_sync.cuh)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -198,6 +198,9 @@ __global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ 
         for (int s = 0; s < X.stages; s++) mbar_init(X.bars + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    pdl_wait_for_previous_step(T.pdl);
+    if (lane == 0) {
         for (int b = 0; b < X.stages && b < X.nboxes; b++) X.arm(b, b);
     }
     __syncwarp();
