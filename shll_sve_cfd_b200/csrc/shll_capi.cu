@@ -409,10 +409,13 @@ int check_connected(shll_ctx *c)
     return SHLL_OK;
 }
 
-// Programmatic dependent launch of the step kernels (halo_sync.cuh): single GPU, outside stream capture.
+// Programmatic dependent launch of the step kernels (halo_sync.cuh), outside stream capture.  Slabs too: a block of step
+// n+1 that is placed early touches nothing but its own halo flag before griddepcontrol.wait returns, i.e. before step n of
+// THIS GPU has completed -- the neighbour-facing protocol (halo_sync.cuh) sees the same order of events as without it.
 int use_pdl(const shll_ctx *c)
 {
-    return (!multi(c) && (!c->capturing || env_int("SHLL_PDL_GRAPH", 0) != 0) && env_int("SHLL_PDL", 1) != 0) ? 1 : 0;
+    if (multi(c) && env_int("SHLL_PDL_MULTI", 1) == 0) return 0;
+    return ((!c->capturing || env_int("SHLL_PDL_GRAPH", 0) != 0) && env_int("SHLL_PDL", 1) != 0) ? 1 : 0;
 }
 
 int launch_one_step(shll_ctx *c)
