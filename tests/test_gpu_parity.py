@@ -258,6 +258,38 @@ def test_cuda_graph_replay_small_grid_matches_single_launches(oracle, monkeypatc
         assert np.array_equal(bits(s.download_u()), bits(ref))
 
 
+@pytest.mark.parametrize("pb", [programs.BASE_SHLL_2D.resized(256, 256), programs.SECOND_ORDER_2D.resized(96, 160),
+                                programs.SECOND_ORDER_1D.resized(200000), programs.BASE_SHLL.resized(200000)],
+                         ids=["2d_o1", "2d_o2", "1d_o2", "1d_o1"])
+def test_programmatic_dependent_launch_does_not_change_bits(pb, monkeypatch):
+    """Every step kernel is launched so that its blocks are placed during the predecessor's tail and wait in
+    griddepcontrol.wait (halo_sync.cuh).  Same bits with the attribute off, in both modes; small grids use thinner chunks."""
+    u0 = _random_state(pb, seed=3)
+    monkeypatch.setenv("SHLL_GRAPH", "0")
+    monkeypatch.setenv("SHLL_PERSIST", "0")
+    for mode in (capi.MODE_STRICT, capi.MODE_FAST):
+        outs = []
+        for pdl in ("1", "0"):
+            monkeypatch.setenv("SHLL_PDL", pdl)
+            with programs.make_solver(pb, mode) as s:
+                s.upload_u(u0)
+                s.run(37)
+                outs.append(s.download_u())
+                assert s.launches == 37
+        assert np.array_equal(bits(outs[0]), bits(outs[1]))
+
+
+def test_small_2d_grids_get_thinner_chunks():
+    """plan_2d shrinks the chunk height until about half the resident warp slots have an item."""
+    def chunks(pb, mode):
+        with programs.make_solver(pb, mode) as s:
+            return int(s.variant.split("_chunks")[1].split("_")[0])
+    assert chunks(programs.SECOND_ORDER_2D.resized(256, 256), capi.MODE_FAST) == 64      # 4-row chunks instead of 64-row ones
+    assert chunks(programs.BASE_SHLL_2D.resized(256, 256), capi.MODE_FAST) == 128        # 2-row chunks
+    assert chunks(programs.BASE_SHLL_2D.resized(4096, 4096), capi.MODE_FAST) == 228      # the tuned 18 rows at configs[2]
+    assert chunks(programs.SECOND_ORDER_2D.resized(2048, 16384), capi.MODE_FAST) == 32   # the tuned 64 rows at configs[4]
+
+
 def test_cfl_diagnostic_and_api_state_errors(oracle):
     pb = programs.BASE_SHLL_2D.resized(64, 64)
     u0 = programs.cons_from_prim(pb, programs.initial_primitives(pb))

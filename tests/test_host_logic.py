@@ -126,3 +126,34 @@ def test_product_package_never_imports_the_oracle():
     for fn in os.listdir(os.path.join(ROOT, "host")):
         if fn.endswith((".c", ".h")) or fn == "Makefile":
             assert "oracle" not in open(os.path.join(ROOT, "host", fn)).read(), fn
+
+
+def test_fetch_local_reads_both_output_formats(tmp_path):
+    """tools/fetch_local.py (the counterpart of the reference's plot script) takes the grid shape from the file."""
+    import importlib.util
+    import numpy as np
+    spec = importlib.util.spec_from_file_location("fetch_local", os.path.join(ROOT, "tools", "fetch_local.py"))
+    fl = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(fl)
+    nx, ny = 6, 4
+    rng = np.random.default_rng(0)
+    p = rng.random((4, nx, ny)).astype(np.float32)
+    with open(tmp_path / "results.dat", "w") as f:          # base_shll_2d.c:322-340
+        for i in range(nx):
+            for j in range(ny):
+                f.write("%e\t%e\t%e\t%e\t%e\t%e\n" % ((i + 0.5) / nx, (j + 0.5) / ny, p[0, i, j], p[1, i, j], p[2, i, j], p[3, i, j]))
+    r = fl.read_any(str(tmp_path / "results.dat"))
+    assert (r["dims"], r["nx"], r["ny"]) == (2, nx, ny)
+    assert np.allclose(r["fields"]["T"], p[3], rtol=1e-6) and np.allclose(r["fields"]["rho"], p[0], rtol=1e-6)
+    hdr = np.zeros(16, dtype="<i4")                           # host/shll_main.c Save_Binary
+    hdr[2:7] = [2, nx, ny, 4, 77]
+    raw = bytearray(hdr.tobytes()); raw[:8] = b"SHLLBIN1"
+    (tmp_path / "snapshot.bin").write_bytes(bytes(raw) + p.tobytes())
+    r = fl.read_any(str(tmp_path / "snapshot.bin"))
+    assert (r["dims"], r["nx"], r["ny"], r["steps"]) == (2, nx, ny, 77) and np.array_equal(r["fields"]["uy"], p[2])
+    with open(tmp_path / "tube.dat", "w") as f:               # base_shll.c:180-192
+        for i in range(9):
+            f.write("%e\t%e\t%e\t%e\n" % ((i + 0.5) / 9, 1.0 + i, 0.5 * i, 2.0))
+    r = fl.read_any(str(tmp_path / "tube.dat"))
+    assert (r["dims"], r["nx"]) == (1, 9) and r["fields"]["u"][4] == 2.0
+    assert "rho" in fl.summary(r) and fl.main([str(tmp_path / "tube.dat"), "--no-plot"]) == 0
