@@ -41,15 +41,16 @@ prof() {  # name regex workload mode [env...]
   python tools/ncu_summary.py $O/${TAG}_$name.ncu-rep $CELLS > $O/${TAG}_$name.ncu.txt 2>&1
   head -8 $O/${TAG}_$name.ncu.txt
 }
-CELLS=16777216
-prof 2d_o1_fast   'step2d_(acc|tma)' 2d_o1 fast   X=1
-prof 2d_o1_strict 'step2d_(acc|tma)' 2d_o1 strict X=1
-CELLS=33554432
-prof 2d_o2_fast   'step2d_(acc|tma)' 2d_o2 fast   X=1
-prof 2d_o2_strict 'step2d_(acc|tma)' 2d_o2 strict X=1
-CELLS=67108864
-prof 1d_o2_fast   'step1d'           1d_o2 fast   X=1
-prof 1d_o1_strict 'step1d'           1d_o1 strict X=1
+WANT=${EVIDENCE_PROFILES:-"2d_o1_fast 2d_o1_strict 2d_o2_fast 2d_o2_strict 1d_o2_fast 1d_o1_strict"}
+for name in $WANT; do
+  case $name in
+    2d_o1_*) CELLS=16777216; rx='step2d_(acc|tma)'; wl=2d_o1 ;;
+    2d_o2_*) CELLS=33554432; rx='step2d_(acc|tma)'; wl=2d_o2 ;;
+    1d_o2_*) CELLS=67108864; rx='step1d'; wl=1d_o2 ;;
+    1d_o1_*) CELLS=67108864; rx='step1d'; wl=1d_o1 ;;
+  esac
+  prof $name "$rx" $wl ${name##*_} X=1
+done
 SZ=$(du -sm $O | cut -f1); echo "gpurun_out is $SZ MiB"
 if [ "$SZ" -gt 55 ]; then rm -f $O/${TAG}_*strict.ncu-rep; echo "dropped the strict .ncu-rep files (summaries kept)"; fi
 echo "== done"
