@@ -213,7 +213,7 @@ __device__ __forceinline__ void row_compute(RowSlot<VEC> &S, const YEdge<VEC> &Y
     if (Y.tile_has_wall) plant_y_ghosts<BC, VEC>(S.u, Y);  // warp-uniform: first / last column tile only
     float hp[VEC][4], hm[VEC][4];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) cell_flux_2d<MODE>(S.u[v], S.fp[v], S.fm[v], hp[v], hm[v]);
+    for (int v = 0; v < VEC; v++) cell_flux_2d<MODE, ORDER == 1>(S.u[v], S.fp[v], S.fm[v], hp[v], hm[v]);
 
     // neighbours across the lane boundary: H+ of cell j-1 ("bottom"), H- of cell j+1 ("top")
     float bottom[VEC][4], top[VEC][4];
