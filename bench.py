@@ -348,6 +348,211 @@ def run_group_arm(args):
     return 0
 
 
+FAST_ARITH_NOTE = ("fast: FP32 state, FP32 + explicit FMA arithmetic in face-flux form; tolerance vs the reference C path on every primitive field, "
+                   "|x - ref| <= tol*(1+|ref|): 3e-5 on the parity configs and on full-size windows (tests/test_gpu_fast_parity.py), full-length runs per "
+                   "tests/conftest.py FAST_TOL_LONG (3e-5 at 1024^2 x 820 steps 1st order; 6e-4 at 256^2 x 1639 steps 2nd order); bitwise independent of the "
+                   "GPU count, tile and chunk geometry")
+STRICT_ARITH_NOTE = "strict: bit-exact vs the reference C path (FP32 + the reference's two double-promoted expressions per cell)"
+MIN_REGION_S = 0.2     # every reported rate comes from >= this much device time (repetitions of the K-step region, median)
+EXTRA_WORKLOADS = {"2d_o2": 100, "1d_o2": 100, "1d_o2_64k": 104858}   # the other BASELINE.json configs: steps per timed region
+
+
+def traffic_entry(key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture (profiles/traffic.json)."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        e = t.get(key)
+        if isinstance(e, dict):
+            return e.get("bytes"), e.get("source")
+        return e, t.get("_source")
+    except Exception:
+        return None, None
+
+
+class Harness:
+    """One process per GPU: barriers, max over ranks, problem set-up for a workload."""
+
+    def __init__(self, args):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist, self.args = torch, dist, args
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        torch.cuda.set_device(self.local_rank)
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, xs):
+        """element-wise max over ranks of a list of floats"""
+        if self.world == 1:
+            return list(xs)
+        t = self.torch.tensor(list(xs), dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return [float(v) for v in t.tolist()]
+
+    def problem(self, workload, nx=0, ny=0, world=None):
+        from dataclasses import replace
+        from shll_sve_cfd_b200 import programs
+        world = self.world if world is None else world
+        w = WORKLOADS[workload]
+        base = programs.PROGRAMS[w["prog"]]
+        nx_per = nx or w["nx"]
+        ny = (ny or w["ny"]) if base.dims == 2 else 1
+        nx_global = nx_per * world if w["scaling"] == "weak" else nx_per
+        pb = base.resized(nx_global, ny) if base.dims == 2 else base.resized(nx_global)
+        if base.dims == 2:
+            # keep DX == DY (so DT_ON_DX == DT_ON_DY == 0.125 as in every reference run): the domain is [0, nx/ny] x [0, 1]
+            pb = replace(pb, lx=float(nx_global) / float(ny), ly=1.0)
+        return pb
+
+    def solver(self, pb, mode):
+        from shll_sve_cfd_b200 import slabs
+        return slabs.SlabSolver(pb, mode, self.dist if self.world > 1 else None, self.rank, self.world, self.local_rank,
+                                gather_device=self.torch.device("cuda", self.local_rank) if self.world > 1 else None)
+
+
+def timed_reps(h, s, K, sampler=None):
+    """Repeat the K-step timed region (CUDA events on the library's stream, barrier + synchronize on both sides of every
+    repetition, max over ranks) until >= MIN_REGION_S of device time has been measured; returns the per-repetition times."""
+    h.barrier()
+    first = h.max_over_ranks([s.run_timed(K)])[0]
+    reps = int(min(2000, max(3, np.ceil(1.1 * MIN_REGION_S * 1e3 / max(first, 1e-4)))))
+    h.barrier()
+    t0 = time.perf_counter()
+    ms = []
+    for _ in range(reps):
+        ms.append(s.run_timed(K))
+        if h.world > 1:
+            h.dist.barrier()
+    h.barrier()
+    t1 = time.perf_counter()
+    ms = h.max_over_ranks(ms)
+    clocks = sampler.window(t0, t1) if sampler is not None else None
+    return ms, clocks, reps
+
+
+def parity_vs_1gpu(h, ss, pb, mode, steps=6):
+    """N-GPU correctness signal inside the bench: the slabs of the benched, full-size problem after `steps` steps from the
+    initial condition, bit for bit against ONE GPU (rank 0's) marching the whole global domain -- compared through one
+    blake2b digest per slab.  The update has no reductions, so the bits may not depend on the decomposition."""
+    import hashlib
+    from shll_sve_cfd_b200 import programs
+    u_loc = ss.initial_state()
+    ss.upload(u_loc)
+    ss.solver.run(steps)
+    out = ss.solver.download_u()
+    digest = hashlib.blake2b(np.ascontiguousarray(out).tobytes(), digest_size=16).hexdigest()
+    parts = [None] * h.world
+    h.dist.all_gather_object(parts, (ss.slab.i0, ss.slab.nx_local, digest))
+    ok = None
+    if h.rank == 0:
+        row = pb.ny if pb.dims == 2 else 1
+        u0 = np.empty((pb.ncomp, pb.nx, row), np.float32)   # slab by slab: the temporaries of a 16384^2 initial condition stay small
+        for i0, nl, _ in parts:
+            u0[:, i0:i0 + nl] = programs.cons_from_prim(pb, programs.initial_primitives(pb, i0=i0, nx_local=nl, nx_global=pb.nx)).reshape(pb.ncomp, nl, row)
+        with programs.make_solver(pb, mode, device=h.local_rank) as s1:
+            s1.upload_u(u0.reshape(pb.ncomp, -1))
+            s1.run(steps)
+            full = s1.download_u(u0.reshape(pb.ncomp, -1)).reshape(pb.ncomp, pb.nx, row)
+        ok = True
+        for i0, nl, dg in parts:
+            mine = hashlib.blake2b(np.ascontiguousarray(full[:, i0:i0 + nl]).tobytes(), digest_size=16).hexdigest()
+            ok = ok and (mine == dg)
+    h.barrier()
+    return ok
+
+
+def measure(h, workload, mode_name, K, W, want_e2e, want_parity, sampler_gpu=None, nx=0, ny=0):
+    """Device-resident rate (median repetition), optional end-to-end rate through the C ABI with pinned host buffers, optional
+    N-GPU bitwise parity, for one workload in one arithmetic mode."""
+    torch = h.torch
+    from shll_sve_cfd_b200 import capi
+    w = WORKLOADS[workload]
+    pb = h.problem(workload, nx, ny)
+    mode = capi.MODE_STRICT if mode_name == "strict" else capi.MODE_FAST
+    ss = h.solver(pb, mode)
+    s = ss.solver
+    ny_ = pb.ny if pb.dims == 2 else 1
+    nloc = ss.slab.nx_local * ny_
+    total_cells = pb.nx * ny_
+    ncomp = pb.ncomp
+    host_in = torch.empty((ncomp, nloc), dtype=torch.float32, pin_memory=True)   # torch is plumbing: pinned allocation, barriers
+    host_in.numpy()[...] = ss.initial_state()
+    u_in = host_in.numpy()
+    sampler = None
+    if sampler_gpu is not None and h.rank == 0:
+        sampler = ClockSampler(sampler_gpu)
+        sampler.start()
+    ss.upload(u_in)
+    s.run(W)
+    s.sync()
+    if sampler is not None:
+        sampler.wait_first()
+    l0 = s.launches
+    ms, clocks, reps = timed_reps(h, s, K, sampler)
+    launches = (s.launches - l0) // (reps + 1)
+    if sampler is not None:
+        sampler.stop()
+    med = float(np.median(ms))
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = w["bpc"] * nloc
+    r = dict(pb=pb, nloc=nloc, total_cells=total_cells, ncomp=ncomp, ms=med, ms_min=float(min(ms)), ms_max=float(max(ms)), reps=reps,
+             region_s=float(sum(ms)) * 1e-3, launches=launches, variant=s.variant, clocks=clocks, grid_per_gpu=[ss.slab.nx_local, ny_],
+             value=total_cells * K / (med * 1e-3), achieved=bytes_per_launch * K / (med * 1e-3) / 1e9, peak=peak, peak_src=peak_src,
+             bytes_per_launch=bytes_per_launch)
+    if want_e2e:
+        # end to end through the C ABI with host buffers: upload + K steps + download inside the timed region
+        host_out = torch.empty((ncomp, nloc), dtype=torch.float32, pin_memory=True)
+        u_out = host_out.numpy()
+        h.barrier()
+        t0 = time.perf_counter()
+        ss.upload(u_in)
+        t_up = time.perf_counter()
+        s.run(K)
+        s.sync()
+        t_run = time.perf_counter()
+        s.download_u(u_out)
+        t_dn = time.perf_counter()
+        h.barrier()
+        t_all = time.perf_counter() - t0
+        t_e2e, up, run, dn = h.max_over_ranks([t_all, t_up - t0, t_run - t_up, t_dn - t_run])
+        nbytes = ncomp * nloc * 4
+        r["e2e"] = {"value": total_cells * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes / K, "d2h_bytes_per_step": nbytes / K,
+                    "seconds": t_e2e, "breakdown_s_max_over_ranks": {"upload": up, "steps": run, "download": dn},
+                    "pcie_gbs_per_gpu": {"h2d": nbytes / up / 1e9, "d2h": nbytes / dn / 1e9},
+                    "note": "one shll_upload_u (pinned host) + K steps + one shll_download_u per run; bytes amortised per step"}
+        r["checksum"] = float(u_out[0].astype(np.float64).sum())
+    if want_parity and h.world > 1:
+        try:
+            r["parity_vs_1gpu"] = parity_vs_1gpu(h, ss, pb, mode)
+        except Exception as ex:   # a failed check is reported, never hidden
+            r["parity_vs_1gpu"] = f"check failed to run: {str(ex)[:160]}"
+    ss.close()
+    return r
+
+
+def workload_block(h, name, r, K):
+    w = WORKLOADS[name]
+    per_launch_note = {}
+    if r["launches"] < K:   # persistent kernel: one launch for all K steps
+        per_launch_note = {"launches_per_region": r["launches"], "us_per_step": r["ms"] * 1e3 / K}
+    tr, tr_src = traffic_entry(f"{name}:fast")
+    return {"description": w["desc"], "scaling": w["scaling"], "grid_global": [r["pb"].nx, r["pb"].ny if r["pb"].dims == 2 else 1],
+            "grid_per_gpu": r["grid_per_gpu"], "kernel": r["variant"], "arith_mode": "fast", "steps": K, "reps": r["reps"],
+            "timed_region_s": r["region_s"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms"] / K,
+            "ms_per_step_min_max": [r["ms_min"] / K, r["ms_max"] / K],
+            "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s", "frac": r["achieved"] / r["peak"],
+                         "traffic": tr, "traffic_source": tr_src, "algorithmic_bytes_per_step": r["bytes_per_launch"]},
+            "clocks": r["clocks"], "parity_vs_1gpu": r.get("parity_vs_1gpu"), **per_launch_note}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -362,6 +567,8 @@ def main():
     ap.add_argument("--ny", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the `workloads` block (the other BASELINE.json configs)")
+    ap.add_argument("--no-parity", action="store_true", help="skip the N-GPU vs 1-GPU bitwise check (N > 1)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -371,150 +578,67 @@ def main():
         return run_reference_arm(args)
 
     import torch
-    import torch.distributed as dist
-    from shll_sve_cfd_b200 import capi, programs, slabs
-
-    rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         print("bench.py: no CUDA device; the product path has no CPU fallback", file=sys.stderr)
         return 2
     if world == 1 and args.gpus > 1:   # no torchrun: one process drives all the GPUs through shll_group_*
         return run_group_arm(args)
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(x: float) -> float:
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
+    h = Harness(args)
+    rank = h.rank
     w = WORKLOADS[args.workload]
-    base = programs.PROGRAMS[w["prog"]]
-    nx_per = args.nx or w["nx"]
-    ny = (args.ny or w["ny"]) if base.dims == 2 else 1
-    nx_global = nx_per * world if w["scaling"] == "weak" else nx_per
-    pb = base.resized(nx_global, ny) if base.dims == 2 else base.resized(nx_global)
-    if base.dims == 2:
-        # keep DX == DY (so DT_ON_DX == DT_ON_DY == 0.125 as in every reference run): the domain is [0, nx/ny] x [0, 1]
-        from dataclasses import replace
-        pb = replace(pb, lx=float(nx_global) / float(ny), ly=1.0)
-    mode = capi.MODE_STRICT if args.mode == "strict" else capi.MODE_FAST
     K, W = args.steps, args.warmup
 
-    ss = slabs.SlabSolver(pb, mode, dist if world > 1 else None, rank, world, local_rank,
-                          gather_device=torch.device("cuda", local_rank) if world > 1 else None)
-    s = ss.solver
-    nloc = ss.slab.nx_local * ny
-    ncomp = pb.ncomp
-    # pinned host buffers (torch is plumbing: pinned allocation, barriers)
-    host_in = torch.empty((ncomp, nloc), dtype=torch.float32, pin_memory=True)
-    host_out = torch.empty((ncomp, nloc), dtype=torch.float32, pin_memory=True)
-    host_in.numpy()[...] = ss.initial_state()
-    u_in, u_out = host_in.numpy(), host_out.numpy()
-
-    # ---- device-resident timing: W warm-up steps, then exactly K timed steps (CUDA events on the library's stream)
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    ss.upload(u_in)
-    s.run(W)
-    s.sync()
-    if rank == 0:
-        sampler.wait_first()
-    barrier()
-    launches0 = s.launches
-    barrier()
-    t_region0 = time.perf_counter()
-    ms = s.run_timed(K)
-    t_region1 = time.perf_counter()
-    barrier()
-    launches = s.launches - launches0
-    ms = max_over_ranks(ms)
-    clocks = None
-    if rank == 0:
-        sampler.stop()
-        clocks = sampler.window(t_region0, t_region1)
-    total_cells = nx_global * ny
-    value = total_cells * K / (ms * 1e-3)
-
-    # ---- end to end through the C ABI with host buffers (upload + K steps + download inside the timed region)
-    e2e = None
-    if not args.no_e2e:
-        barrier()
-        t0 = time.perf_counter()
-        ss.upload(u_in)
-        s.run(K)
-        s.download_u(u_out)
-        barrier()
-        t_e2e = max_over_ranks(time.perf_counter() - t0)
-        nbytes = ncomp * nloc * 4
-        e2e = {"value": total_cells * K / t_e2e, "unit": UNIT, "h2d_bytes_per_step": nbytes / K, "d2h_bytes_per_step": nbytes / K,
-               "seconds": t_e2e, "note": "one shll_upload_u (pinned host) + K steps + one shll_download_u per run; bytes amortised per step"}
-        checksum = float(u_out[0].astype(np.float64).sum())
-    variant = s.variant
-    ss.close()
-
+    # ---- the headline workload: device-resident rate, end to end, N-GPU parity
+    r = measure(h, args.workload, args.mode, K, W, want_e2e=not args.no_e2e, want_parity=not args.no_parity,
+                sampler_gpu=h.local_rank, nx=args.nx, ny=args.ny)
     # ---- the other arithmetic mode, device-resident timing only (same workload, same K)
     other = None
     if not args.no_other_mode:
-        omode = capi.MODE_STRICT if mode == capi.MODE_FAST else capi.MODE_FAST
-        so = slabs.SlabSolver(pb, omode, dist if world > 1 else None, rank, world, local_rank,
-                              gather_device=torch.device("cuda", local_rank) if world > 1 else None)
-        so.upload(u_in)
-        so.solver.run(W)
-        so.solver.sync()
-        barrier()
-        oms = max_over_ranks(so.solver.run_timed(K))
-        barrier()
-        other = {"arith_mode": "strict" if omode == capi.MODE_STRICT else "fast", "kernel": so.solver.variant,
-                 "value": total_cells * K / (oms * 1e-3), "unit": UNIT, "ms_per_step": oms / K,
-                 "roofline_frac": (w["bpc"] * nloc / (oms * 1e-3 / K) / 1e9) / measured_peak_gbs()[0]}
-        so.close()
+        omode = "strict" if args.mode == "fast" else "fast"
+        o = measure(h, args.workload, omode, K, W, want_e2e=False, want_parity=False, nx=args.nx, ny=args.ny)
+        other = {"arith_mode": omode, "kernel": o["variant"], "value": o["value"], "unit": UNIT, "ms_per_step": o["ms"] / K,
+                 "reps": o["reps"], "roofline_frac": o["achieved"] / o["peak"]}
+    # ---- the other BASELINE.json configs, FAST, each over >= MIN_REGION_S of device time
+    blocks = {}
+    custom = bool(args.nx or args.ny)
+    if not args.no_workloads and not custom:
+        for name, kw in EXTRA_WORKLOADS.items():
+            if name == args.workload or (name == "1d_o2_64k" and world > 1):
+                continue
+            try:
+                rw = measure(h, name, "fast", kw, 10, want_e2e=False, want_parity=not args.no_parity, sampler_gpu=h.local_rank)
+                blocks[name] = workload_block(h, name, rw, kw)
+            except Exception as ex:
+                blocks[name] = {"error": str(ex)[:300]}
 
     if rank == 0:
-        peak, peak_src = measured_peak_gbs()
-        bytes_per_launch = w["bpc"] * nloc
-        achieved = bytes_per_launch / (ms * 1e-3 / K) / 1e9
-        traffic = None
-        tr_path = os.path.join(ROOT, "profiles", "traffic.json")
-        if os.path.exists(tr_path):
-            try:
-                traffic = json.load(open(tr_path)).get(f"{args.workload}:{args.mode}")
-            except Exception:
-                traffic = None
-        state_bytes = ncomp * nloc * 4
+        tr, tr_src = traffic_entry(f"{args.workload}:{args.mode}")
+        state_bytes = r["ncomp"] * r["nloc"] * 4
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": ms / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
+            "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": r["ms"] / K, "higher_is_better": True, "scaling": w["scaling"], "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "description": w["desc"], "grid_global": [nx_global, ny],
-                       "grid_per_gpu": [ss.slab.nx_local, ny], "kernel": variant,
-                       "arith_mode": ("fast: FP32 state, FP32 + explicit FMA arithmetic, within 3e-5 of the reference C path (tests/test_gpu_parity.py); "
-                                      "bitwise independent of the GPU count" if mode == capi.MODE_FAST else
-                                      "strict: bit-exact vs the reference C path (FP32 + the reference's two double-promoted expressions per cell)"),
+            "config": {"workload": args.workload, "description": w["desc"], "grid_global": [r["pb"].nx, r["pb"].ny if r["pb"].dims == 2 else 1],
+                       "grid_per_gpu": r["grid_per_gpu"], "kernel": r["variant"],
+                       "arith_mode": FAST_ARITH_NOTE if args.mode == "fast" else STRICT_ARITH_NOTE,
                        "parallelism": f"slab{world}" if world > 1 else "single",
+                       "timing": f"the K-step region repeated {r['reps']} times ({r['region_s']:.3f} s of device time, CUDA events, max over ranks per "
+                                 f"repetition); value = median repetition; min/max ms per step {r['ms_min'] / K:.5f}/{r['ms_max'] / K:.5f}",
                        "l2": "inputs larger than L2 (no flush needed)" if state_bytes > L2_BYTES else "state fits in L2 (resident between steps by design)"},
-            "gpu_launches": launches,
-            "e2e": e2e,
+            "gpu_launches": r["launches"],
+            "reps": r["reps"], "timed_region_s": r["region_s"],
+            "e2e": r.get("e2e"),
             "other_mode": other,
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": bytes_per_launch, "kernel": variant},
-            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s", "frac": r["achieved"] / r["peak"],
+                         "traffic": tr, "traffic_source": tr_src, "peak_source": r["peak_src"],
+                         "algorithmic_bytes_per_launch": r["bytes_per_launch"], "kernel": r["variant"]},
+            "clocks": r["clocks"],
+            "parity_vs_1gpu": r.get("parity_vs_1gpu"),
+            "workloads": blocks,
         }
-        if not args.no_e2e:
-            line["config"]["e2e_checksum_rho"] = checksum
+        if "checksum" in r:
+            line["config"]["e2e_checksum_rho"] = r["checksum"]
         if world == 1 and not args.no_cpu_baseline:
             try:
                 cb = cpu_reference_rate(args.workload)
@@ -527,7 +651,7 @@ def main():
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": f"failed: {ex}"}
         print(json.dumps(line))
     if world > 1:
-        dist.destroy_process_group()
+        h.dist.destroy_process_group()
     return 0
 
 

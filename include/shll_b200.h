@@ -133,6 +133,14 @@ SHLL_API long shll_launch_count(const shll_ctx *ctx);
 /* Name of the kernel variant the context selected, for logs. */
 SHLL_API const char *shll_variant_name(const shll_ctx *ctx);
 
+/* Device self-test of the STRICT-mode exactness shortcuts (csrc/shll_math.cuh: shared-reciprocal float division,
+ * division by the constant CV in double): `npairs` operand pairs drawn on the device (uniform bit patterns, physical
+ * magnitudes, the guard edges, denormals, signed zeros, infinities, NaNs) are compared bit for bit with the IEEE
+ * divisions the reference executes (base_shll.c:173-175, base_shll_2d.c:314-316).  counts[0..3] = mismatches of
+ * div_rn_shared / div_rn_spec / div_by_cv / div_by_cv_spec (all must be 0), [4],[5] = draws the one-guard-per-cell forms
+ * flagged for IEEE recomputation, [6] = draws that left div_rn_shared's fast path, [7],[8] = float pairs / doubles tested. */
+SHLL_API int shll_selftest_exact_division(int device, unsigned long long npairs, unsigned long long seed, unsigned long long counts[9]);
+
 /* ---- multi-GPU slabs (one context per GPU, same or different processes) -------------------------
  * Each context exports a 64-byte CUDA-IPC handle per resource; the host exchanges them (MPI,
  * torch.distributed, a pipe ...) and connects each context to its lower (rank-1) and upper (rank+1)

@@ -21,7 +21,7 @@ IPC_BYTES = 64
 API_SYMBOLS = [
     "shll_abi_version", "shll_last_error", "shll_count_steps", "shll_create", "shll_destroy", "shll_upload_u",
     "shll_download_u", "shll_download_p", "shll_run", "shll_sync", "shll_run_timed", "shll_max_cfl",
-    "shll_conserved_sums",
+    "shll_conserved_sums", "shll_selftest_exact_division",
     "shll_launch_count", "shll_variant_name", "shll_peer_export", "shll_peer_connect",
     "shll_group_create", "shll_group_destroy", "shll_group_last_error", "shll_group_size", "shll_group_ctx",
     "shll_group_upload_u", "shll_group_download_u", "shll_group_download_p", "shll_group_run", "shll_group_run_timed",
@@ -81,6 +81,7 @@ def lib():
         L.shll_run_timed.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_float)]
         L.shll_max_cfl.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.shll_conserved_sums.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.shll_selftest_exact_division.argtypes = [C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
         L.shll_launch_count.restype = C.c_long
         L.shll_launch_count.argtypes = [C.c_void_p]
         L.shll_variant_name.restype = C.c_char_p
@@ -113,6 +114,17 @@ def count_steps(dt, total_time) -> int:
     if rc:
         raise ShllError(rc, lib().shll_last_error(None).decode())
     return n.value
+
+
+def selftest_exact_division(npairs: int, seed: int = 1, device: int = 0) -> dict:
+    """Device self-test of the STRICT exactness shortcuts against IEEE division (csrc/selftest.cu)."""
+    c = (C.c_ulonglong * 9)()
+    rc = lib().shll_selftest_exact_division(int(device), int(npairs), int(seed), c)
+    if rc:
+        raise ShllError(rc, "shll_selftest_exact_division failed")
+    keys = ("div_rn_shared_mismatch", "div_rn_spec_mismatch", "div_by_cv_mismatch", "div_by_cv_spec_mismatch",
+            "float_flagged", "double_flagged", "float_slow_path", "float_pairs", "doubles")
+    return dict(zip(keys, [int(v) for v in c]))
 
 
 def _ptrs(arr: np.ndarray):

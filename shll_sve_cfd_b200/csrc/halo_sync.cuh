@@ -55,22 +55,30 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-// Whole warp calls this; lane 0 spins.
+// Whole warp calls this; lane 0 spins.  The error word is sticky: once ANY wait of this context has timed out (a dead
+// neighbour never posts a later flag either), every later wait -- the other edge warps of this step and all the steps
+// already enqueued behind it -- returns at once, so a lost neighbour costs ONE timeout, not one per edge warp per step.
+// The halo rows come from the peer GPU through the generic proxy; the TMA kernels read them through the async proxy, so
+// the acquire is followed by a proxy fence (edge warps only: 2*ntiles warps per step).
 __device__ __forceinline__ void halo_wait(const HaloSync &S, const unsigned *flag)
 {
     if (flag == nullptr) return;
     if ((threadIdx.x & 31) == 0) {
-        if ((int)(ld_acquire_sys(flag) - S.want) < 0) {
+        if ((int)(ld_acquire_sys(flag) - S.want) < 0 && *(volatile unsigned *)S.err == 0u) {
             const unsigned long long t0 = globaltimer_ns();
             unsigned polls = 0;
             while ((int)(ld_acquire_sys(flag) - S.want) < 0) {
                 __nanosleep(32);
-                if ((++polls & 255u) == 0 && globaltimer_ns() - t0 > S.timeout_ns) {
-                    atomicExch(S.err, 1u);
-                    break;
+                if ((++polls & 15u) == 0) {
+                    if (*(volatile unsigned *)S.err != 0u) break;
+                    if ((polls & 255u) == 0 && globaltimer_ns() - t0 > S.timeout_ns) {
+                        atomicExch(S.err, 1u);
+                        break;
+                    }
                 }
             }
         }
+        asm volatile("fence.proxy.async;" ::: "memory");
     }
     __syncwarp();
 }

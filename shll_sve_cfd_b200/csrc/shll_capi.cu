@@ -69,6 +69,7 @@ struct shll_ctx {
     unsigned *round_done;
     unsigned persist_rounds;  // value of round_done[] after the last persistent launch
     int persist_blocks, persist_threads, persist_K;
+    bool persist_failed;      // allocation or cooperative launch failed once: use the per-step kernels from now on
     int tma_stages;
     size_t tma_smem;
     char variant[128];
@@ -114,15 +115,16 @@ int env_int(const char *name, int dflt)
     return (s && *s) ? atoi(s) : dflt;
 }
 
-// Choose vector width, tiles and row chunks for the 2D kernel.
-void plan_2d(shll_ctx *c)
+// Choose vector width, tiles and row chunks for the 2D kernel.  no_tma: the caller has already found that the TMA
+// descriptors cannot be made (plan again for the LDG kernel; never decided through the environment).
+void plan_2d(shll_ctx *c, bool no_tma = false)
 {
     const shll_config &g = c->cfg;
     int vec = g.variant > 0 ? g.variant : env_int("SHLL_VEC", 0);
     if (vec != 1 && vec != 2 && vec != 4) vec = (g.order == 1) ? 2 : 1;  // defaults from the B200 sweep in DESIGN.md
     while (vec > 1 && (g.ny % vec != 0 || g.ny < 32 * vec)) vec >>= 1;
     // TMA-fed kernel (step2d_tma.cuh) whenever the row stride is a multiple of 16 bytes; SHLL_TMA=0 forces the LDG kernel.
-    c->key.tma = (g.ny % 4 == 0) && (g.ny >= 32) && env_int("SHLL_TMA", 1) != 0;
+    c->key.tma = !no_tma && (g.ny % 4 == 0) && (g.ny >= 32) && env_int("SHLL_TMA", 1) != 0;
     if (c->key.tma) {
         // defaults from the B200 sweep (profiles/r01_sweep_2d.log): order 1 FAST 2 cells per lane, everything else 1
         if (g.variant <= 0 && env_int("SHLL_VEC", 0) <= 0) vec = (g.mode == SHLL_MODE_FAST) ? 2 : 1;
@@ -193,13 +195,6 @@ int make_tensor_maps(shll_ctx *c)
     c->tma_smem = (size_t)c->tma_stages * stage_stride + 8 * c->tma_stages;
     if (c->key.acc && g.order == 2 && c->key.acc_cfg >= 2) c->tma_smem += (c->key.acc_cfg == 4 ? 2048 : 4096) + 16;  // per-warp stash (step2d_acc.cuh)
     return 0;
-}
-
-void plan_2d_fallback(shll_ctx *c)
-{
-    setenv("SHLL_TMA", "0", 1);
-    plan_2d(c);
-    unsetenv("SHLL_TMA");
 }
 
 void plan_1d(shll_ctx *c)
@@ -315,8 +310,7 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     if (g.dims == 2 && c->key.tma) {
         int rc = make_tensor_maps(c);
         if (rc != 0) {  // not fatal: the LDG kernel computes the same bits
-            c->key.tma = false;
-            plan_2d_fallback(c);
+            plan_2d(c, /*no_tma=*/true);
         }
     }
     snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? (c->key.acc ? "_tma_acc" : "_tma") : ((g.dims == 1 && c->key.acc) ? "_acc" : ""),
@@ -415,6 +409,13 @@ int check_connected(shll_ctx *c)
 int use_pdl(const shll_ctx *c)
 {
     if (multi(c) && env_int("SHLL_PDL_MULTI", 1) == 0) return 0;
+    // 1D step kernels let their successor be placed BEFORE their halo wait (step1d.cuh: launch_dependents first).  When two
+    // slabs share one device (shll_group with a device listed twice) the parked successors of a slab that is waiting for
+    // its neighbour could take the SM slots that neighbour needs: no programmatic launch there.  (2D kernels wait for the
+    // halo before launch_dependents, so at most ~2 of their grids are ever resident.)
+    if (multi(c) && c->cfg.dims == 1)
+        for (int s = 0; s < 2; s++)
+            if (c->connected[s] && c->peer_desc[s].pid == (int64_t)getpid() && c->peer_desc[s].device == c->cfg.device) return 0;
     return ((!c->capturing || env_int("SHLL_PDL_GRAPH", 0) != 0) && env_int("SHLL_PDL", 1) != 0) ? 1 : 0;
 }
 
@@ -530,10 +531,21 @@ int run_persistent_1d(shll_ctx *c, long nsteps)
         const int seg_max = (g.nx + nb - 1) / nb;
         const int threads = ((seg_max + 2 * h + 31) / 32) * 32;
         if (threads > 1024 || g.nx < 2 * h) return SHLL_E_STATE;  // too many cells for one cell per thread: streaming kernel
+        // the context becomes "persistent" only once everything it needs exists
+        float *strips = nullptr;
+        unsigned *round_done = nullptr;
+        cudaError_t ea = cudaMalloc(&strips, (size_t)2 * nb * 2 * 3 * h * sizeof(float));
+        if (ea == cudaSuccess) ea = cudaMalloc(&round_done, (size_t)nb * sizeof(unsigned));
+        if (ea == cudaSuccess) ea = cudaMemsetAsync(round_done, 0, (size_t)nb * sizeof(unsigned), c->stream);
+        if (ea != cudaSuccess) {
+            if (strips) cudaFree(strips);
+            if (round_done) cudaFree(round_done);
+            (void)cudaGetLastError();
+            c->persist_failed = true;
+            return SHLL_E_STATE;  // the per-step kernels need no extra memory: fall through to them
+        }
+        c->strips = strips; c->round_done = round_done;
         c->persist_blocks = nb; c->persist_threads = threads; c->persist_K = K;
-        CK(c, cudaMalloc(&c->strips, (size_t)2 * nb * 2 * 3 * h * sizeof(float)));
-        CK(c, cudaMalloc(&c->round_done, (size_t)nb * sizeof(unsigned)));
-        CK(c, cudaMemsetAsync(c->round_done, 0, (size_t)nb * sizeof(unsigned), c->stream));
         c->persist_rounds = 0;
     }
     Persist1DParams P;
@@ -548,7 +560,13 @@ int run_persistent_1d(shll_ctx *c, long nsteps)
     P.quarter = 0.25f;
     P.timeout_ns = (unsigned long long)env_int("SHLL_HALO_TIMEOUT_MS", 5000) * 1000000ull;
     cudaError_t e = launch_persist1d(c->key, P, c->persist_blocks, c->persist_threads, c->stream);
-    if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "persistent 1D launch failed: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess) {
+        // e.g. cudaErrorCooperativeLaunchTooLarge under MPS / a reduced SM count: nothing has run, so clear the launch error,
+        // never try again on this context and let shll_run take the launch-per-step path.
+        (void)cudaGetLastError();
+        c->persist_failed = true;
+        return SHLL_E_STATE;
+    }
     const long nrounds = (nsteps + c->persist_K - 1) / c->persist_K;
     c->persist_rounds += (unsigned)(nrounds - 1);
     c->cur = outb;
@@ -650,7 +668,7 @@ int shll_run(shll_ctx *c, long nsteps)
     int rc = check_connected(c);
     if (rc) return rc;
     // Launch-bound regime, 1D: one cooperative launch keeps every cell in a register for all nsteps (persist1d.cuh).
-    if (c->cfg.dims == 1 && !multi(c) && nsteps >= 32 && env_int("SHLL_PERSIST", 1) != 0) {
+    if (c->cfg.dims == 1 && !multi(c) && nsteps >= 32 && !c->persist_failed && env_int("SHLL_PERSIST", 1) != 0) {
         rc = run_persistent_1d(c, nsteps);
         if (rc != SHLL_E_STATE) return rc;  // SHLL_E_STATE here means "not eligible": fall through to the launch-per-step paths
     }

@@ -373,3 +373,19 @@ def test_1d_64m_cells_fixed_step_count_window_vs_oracle(oracle):
     assert np.array_equal(bits(got[:, i0 + m:i0 + W - m]), bits(ref[:, m:W - m]))
     # far from the diaphragm nothing may have changed
     assert np.array_equal(bits(got[:, :1000]), bits(u0[:, :1000]))
+
+
+def test_exactness_shortcuts_device_selftest():
+    """STRICT mode never executes nvcc's division expansion on the hot path (csrc/shll_math.cuh: div_rn_shared / div_rn_spec /
+    div_by_cv / div_by_cv_spec).  csrc/selftest.cu runs those sequences on the device against __fdiv_rn / __ddiv_rn over 2^28
+    operand pairs (uniform bit patterns, physical magnitudes, the guard edges 2^+-60 / 2^+-40, denormals, signed zeros,
+    infinities, NaNs): not one bit may differ.  The exact-rational-arithmetic twin is in tests/test_host_logic.py."""
+    r = capi.selftest_exact_division(1 << 28, seed=2026)
+    assert r["float_pairs"] >= (1 << 28) and r["doubles"] >= (1 << 28), r
+    assert r["div_rn_shared_mismatch"] == 0 and r["div_rn_spec_mismatch"] == 0, r
+    assert r["div_by_cv_mismatch"] == 0 and r["div_by_cv_spec_mismatch"] == 0, r
+    # the guards are exercised on both sides: most draws stay on the fast path, a real share leaves it
+    assert 0 < r["float_flagged"] < r["float_pairs"] // 2 and 0 < r["double_flagged"] < r["doubles"] // 4, r
+    assert 0 < r["float_slow_path"] < r["float_pairs"] // 2, r
+    r2 = capi.selftest_exact_division(1 << 22, seed=7)
+    assert sum(r2[k] for k in r2 if k.endswith("mismatch")) == 0, r2

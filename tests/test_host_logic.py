@@ -157,3 +157,106 @@ def test_fetch_local_reads_both_output_formats(tmp_path):
     r = fl.read_any(str(tmp_path / "tube.dat"))
     assert (r["dims"], r["nx"]) == (1, 9) and r["fields"]["u"][4] == 2.0
     assert "rho" in fl.summary(r) and fl.main([str(tmp_path / "tube.dat"), "--no-plot"]) == 0
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# STRICT-mode exactness shortcuts (csrc/shll_math.cuh) in exact rational arithmetic.  The device twin -- the same
+# sequences executed by the GPU against __fdiv_rn / __ddiv_rn over 2^28 operand pairs -- is
+# tests/test_gpu_parity.py::test_exactness_shortcuts_device_selftest (csrc/selftest.cu).
+
+def _rn(F, p, emin):
+    """Round the rational F to the nearest binary floating-point number with p significand bits (ties to even), gradual
+    underflow below 2^emin; returned as an exact Fraction."""
+    from fractions import Fraction
+    if F == 0:
+        return Fraction(0)
+    s = -1 if F < 0 else 1
+    F = abs(F)
+    e = F.numerator.bit_length() - F.denominator.bit_length()
+    if Fraction(2) ** e > F:
+        e -= 1
+    e = max(e, emin)
+    scale = Fraction(2) ** (e - (p - 1))
+    m = F / scale
+    fl = m.numerator // m.denominator
+    r = m - fl
+    if r > Fraction(1, 2) or (r == Fraction(1, 2) and fl % 2 == 1):
+        fl += 1
+    return s * fl * scale
+
+
+def _markstein_chunk(args):
+    """div_by_cv (shll_math.cuh:100-114) on `count` doubles: q = RN(n*rc); rem = RN(n - CV*q); q' = RN(q + rem*rc) must equal
+    RN(n / CV).  float(Fraction) is correctly rounded in CPython, so every RN53 here is exact."""
+    import random
+    import struct
+    from fractions import Fraction
+    seed, count = args
+    CV = float(np.float32(1.0 / (float(np.float32(1.4)) - 1.0)))
+    rc = float.fromhex("0x1.9999970a3d74cp-2")
+    FCV, Frc = Fraction(CV), Fraction(rc)
+    rng = random.Random(seed)
+    bad, done = [], 0
+    while done < count:
+        kind = rng.random()
+        if kind < 0.5:      # uniform bit patterns inside the guarded exponent range
+            n = struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0]
+        elif kind < 0.9:    # the operands the kernels produce: (double)e - 0.5*(double)k of float32 e, k of a gas state
+            e, k = np.float32(rng.uniform(0.1, 50.0)), np.float32(rng.uniform(0.0, 20.0))
+            n = float(e) - 0.5 * float(k)
+        else:               # the guard edges |n| ~ 2^-969 and 2^976, and values whose quotient sits next to a rounding boundary
+            ex = rng.choice([-968, -967, -900, -1, 0, 1, 900, 974, 975])
+            n = (1.0 + rng.getrandbits(52) * 2.0 ** -52) * 2.0 ** ex * rng.choice([-1.0, 1.0])
+        if n != n or abs(n) == float("inf") or abs(n) < 2.0 ** -968 or abs(n) > 2.0 ** 976:
+            continue        # outside the guard: the kernel executes __ddiv_rn there
+        q = n * rc
+        rem = float(Fraction(n) - FCV * Fraction(q))
+        q2 = float(Fraction(rem) * Frc + Fraction(q))
+        if q2 != float(Fraction(n) / FCV):
+            bad.append(n)
+        done += 1
+    return bad
+
+
+def test_division_by_cv_markstein_sequence_is_correctly_rounded_in_exact_arithmetic():
+    """>= 10^6 random + boundary doubles: the multiply + Markstein correction equals RN53(n / CV) in exact rational arithmetic."""
+    import multiprocessing as mp
+    from fractions import Fraction
+    CV = float(np.float32(1.0 / (float(np.float32(1.4)) - 1.0)))
+    assert CV == 2.5000002384185791015625 and float(1 / Fraction(CV)) == float.fromhex("0x1.9999970a3d74cp-2")   # rc = RN53(1/CV)
+    nproc = max(1, min(8, (os.cpu_count() or 2) // 2))
+    chunks = [(1000 + i, 1_000_000 // 40) for i in range(40)]
+    with mp.get_context("fork").Pool(nproc) as pool:
+        bad = [n for part in pool.map(_markstein_chunk, chunks) for n in part]
+    assert not bad, f"{len(bad)} of 1e6 quotients are not correctly rounded, e.g. n = {bad[0].hex()}"
+
+
+def test_shared_reciprocal_float_division_is_correctly_rounded_in_exact_arithmetic():
+    """div_rn_shared / div_rn_spec (shll_math.cuh:76-98,124-140): with ANY starting reciprocal within 1 ulp of 1/b (MUFU.RCP's
+    bound), one Newton step + quotient + remainder + correction gives RN24(a / b) whenever the guard holds
+    (|b| in [2^-60, 2^60], |q0| in [2^-40, 2^40])."""
+    import random
+    from fractions import Fraction
+    rng = random.Random(7)
+    R24 = lambda F: _rn(F, 24, -126)
+
+    def f32(ex):
+        return Fraction(rng.choice([-1, 1]) * (2 ** 23 + rng.getrandbits(23))) * Fraction(2) ** (ex - 23)
+
+    bad = 0
+    for _ in range(60000):
+        kind = rng.random()
+        b = f32(rng.randint(-60, 59)) if kind < 0.3 else f32(rng.randint(-10, 10))
+        a = f32(rng.randint(-80, 80)) if kind < 0.3 else f32(rng.randint(-20, 20))
+        r0 = R24(1 / b)
+        ulp = Fraction(2) ** ((abs(r0).numerator.bit_length() - abs(r0).denominator.bit_length()) - 23)
+        r0 = r0 + rng.choice([-1, 0, 0, 1]) * ulp          # MUFU.RCP: within 1 ulp, not necessarily correctly rounded
+        e = R24(1 - b * r0)
+        r = R24(r0 + r0 * e)
+        q0 = R24(a * r)
+        if not (Fraction(2) ** -40 <= abs(q0) <= Fraction(2) ** 40):
+            continue                                       # the kernel executes __fdiv_rn there
+        rem = R24(a - b * q0)
+        q = R24(q0 + r * rem)
+        bad += (q != R24(a / b))
+    assert bad == 0
