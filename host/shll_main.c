@@ -1,12 +1,16 @@
 /*
  * shll_main.c -- C host program: the reference's program contract on top of libshll_b200.so.
  *
- * One source, four executables (host/Makefile), each a drop-in for one reference program:
+ * One source, five executables (host/Makefile), each a drop-in for one reference program:
  *
  *   -DPROGRAM=1  base_shll               base-c/base_shll.c            1D Sod, 1st order, reflective, N=256, t=0.2
  *   -DPROGRAM=2  base_shll_2d            base-c/base_shll_2d.c         2D implosion, 1st order, reflective, 256^2, t=0.1
  *   -DPROGRAM=3  2nd_order_base_shll     base-c/2nd_order_base_shll.c  2D four-shock, 2nd order (minmod), outflow, 256^2, t=0.8
  *   -DPROGRAM=4  2nd_order_base_shll_1d  derived: the x-sweep of program 3 on a 1D Sod tube, t=0.2
+ *   -DPROGRAM=5  base_omp_2nd_order      base-omp/2nd_order_base_shll.c  2D "configuration 6", 2nd order with the MC limiter
+ *                                        (alpha = 1.25, :44,317-325), outflow, 1024^2, t=0.3 (README Tables 16/17).  The
+ *                                        reference prints `Completed in %d steps` once per OpenMP thread and hard-codes 16
+ *                                        threads (:620,652): this program prints the line 16 times too (SHLL_OMP_LINES=n).
  *
  * Same shape as the reference's main() (base_shll.c:198-225): Allocate_and_Init_Memory, Compute_U_from_P, the float
  * clock, `Completed in %d steps`, Save_Results (results.dat), Free_Memory.  The three calls inside the reference's time
@@ -60,6 +64,13 @@
 #define DEFAULT_NX 256
 #define DEFAULT_TOTAL_TIME 0.8
 #define SAVE_BY_DEFAULT 0 /* commented out in 2nd_order_base_shll.c:588 */
+#elif PROGRAM == 5
+#define DIMS 2
+#define ORDER 2
+#define BC SHLL_BC_OUTFLOW
+#define DEFAULT_NX 1024        /* base-omp/2nd_order_base_shll.c:29-31 */
+#define DEFAULT_TOTAL_TIME 0.3 /* :43 */
+#define SAVE_BY_DEFAULT 0      /* commented out in base-omp/2nd_order_base_shll.c:654 */
 #else
 #define DIMS 1
 #define ORDER 2
@@ -67,6 +78,11 @@
 #define DEFAULT_NX 256
 #define DEFAULT_TOTAL_TIME 0.2
 #define SAVE_BY_DEFAULT 1
+#endif
+#if PROGRAM == 5
+#define LIMITER SHLL_LIM_MC /* base-omp/2nd_order_base_shll.c:317-325 */
+#else
+#define LIMITER SHLL_LIM_MINMOD
 #endif
 #define NCOMP (DIMS == 1 ? 3 : 4)
 
@@ -116,6 +132,13 @@ void Allocate_and_Init_Memory(void)
 #elif PROGRAM == 2
             int inside = (i > 0.2 * NX) && (i < 0.8 * NX) && (j > 0.2 * NY) && (j < 0.8 * NY);
             rho = inside ? 1.0 : 10.0; /* implosion, base_shll_2d.c:96-100 */
+#elif PROGRAM == 5
+            /* "Configuration 6", base-omp/2nd_order_base_shll.c:149-167 (cells exactly on a 1/2 line fall to the last state) */
+            int lo_i = i < 0.5 * NX, hi_i = i > 0.5 * NX, lo_j = j < 0.5 * NY, hi_j = j > 0.5 * NY;
+            if (lo_i && lo_j)      { rho = 1.0; vx = -0.75; vy = 0.5;  T = (1.0 / (rho * R)); }
+            else if (hi_i && lo_j) { rho = 3.0; vx = -0.75; vy = -0.5; T = (1.0 / (rho * R)); }
+            else if (lo_i && hi_j) { rho = 2.0; vx = 0.75;  vy = 0.5;  T = (1.0 / (rho * R)); }
+            else                   { rho = 1.0; vx = 0.75;  vy = -0.5; T = (1.0 / (rho * R)); }
 #else
             /* Euler four-shock problem, 2nd_order_base_shll.c:137-145 (cells exactly on a 3/4 line fall to the last state) */
             int lo_i = i < 0.75 * NX, hi_i = i > 0.75 * NX, lo_j = j < 0.75 * NY, hi_j = j > 0.75 * NY;
@@ -247,7 +270,7 @@ int main(int argc, char **argv)
     memset(&cfg, 0, sizeof(cfg));
     cfg.struct_size = sizeof(cfg);
     cfg.dims = DIMS; cfg.nx = NX; cfg.ny = NY; cfg.order = ORDER; cfg.bc = BC;
-    cfg.limiter = SHLL_LIM_MINMOD; cfg.alpha = 1.25f;
+    cfg.limiter = LIMITER; cfg.alpha = 1.25f; /* alpha: base-omp/2nd_order_base_shll.c:44 */
     cfg.tform = (PROGRAM == 4) ? SHLL_TFORM_2D : SHLL_TFORM_AUTO;
     cfg.mode = (getenv("SHLL_MODE") && !strcmp(getenv("SHLL_MODE"), "fast")) ? SHLL_MODE_FAST : SHLL_MODE_STRICT;
     cfg.dt_on_dx = DT_ON_DX; cfg.dt_on_dy = DT_ON_DY;
@@ -276,7 +299,11 @@ int main(int argc, char **argv)
     }
     Run_Time_Steps();
 
-    printf("Completed in %d steps\n", NO_STEPS);
+    int lines = 1;
+#if PROGRAM == 5
+    lines = getenv("SHLL_OMP_LINES") ? atoi(getenv("SHLL_OMP_LINES")) : 16; /* one line per OpenMP thread, base-omp/...:620,652 */
+#endif
+    for (int l = 0; l < lines; l++) printf("Completed in %d steps\n", NO_STEPS);
     int save = getenv("SHLL_SAVE") ? atoi(getenv("SHLL_SAVE")) : SAVE_BY_DEFAULT;
     if (save) Save_Results();
     if (getenv("SHLL_SAVE_BIN") && atoi(getenv("SHLL_SAVE_BIN"))) Save_Binary("results.bin", NO_STEPS);

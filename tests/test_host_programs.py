@@ -104,3 +104,13 @@ def test_binary_dump_snapshots_and_monitor(manifest, tmp_path):
     assert max(mass) - min(mass) < 1e-6 * mass[0]                       # reflective walls conserve mass
     cfl = [float(l.split("max CFL")[1].split()[0]) for l in mon]
     assert all(0.1 < c < 0.5 for c in cfl)
+
+
+def test_base_omp_second_order_mc_limiter(manifest, tmp_path):
+    """-DPROGRAM=5: drop-in for base-omp/2nd_order_base_shll.c (MC limiter alpha = 1.25, configuration-6 IC, t = 0.3;
+    `Completed in %d steps` once per OpenMP thread, 16 threads hard-coded in the reference)."""
+    out = _run("base_omp_2nd_order", [64], tmp_path, env={"SHLL_SAVE": "1"})
+    assert out == "Completed in 154 steps\n" * 16 + "Saving to file\nCompleted saving data\n"
+    assert _md5(os.path.join(tmp_path, "results.dat")) == manifest["omp_o2_64"]["results_dat_md5"]
+    out = _run("base_omp_2nd_order", [128], tmp_path, env={"SHLL_OMP_LINES": "1"})
+    assert out == "Completed in 308 steps\n"          # Save_Results is commented out in the reference's main()
