@@ -350,7 +350,7 @@ def run_group_arm(args):
 
 FAST_ARITH_NOTE = ("fast: FP32 state, FP32 + explicit FMA arithmetic in face-flux form; tolerance vs the reference C path on every primitive field, "
                    "|x - ref| <= tol*(1+|ref|): 3e-5 on the parity configs and on full-size windows (tests/test_gpu_fast_parity.py), full-length runs per "
-                   "tests/conftest.py FAST_TOL_LONG (3e-5 at 1024^2 x 820 steps 1st order; 6e-4 at 256^2 x 1639 steps 2nd order); bitwise independent of the "
+                   "tests/conftest.py FAST_TOL_LONG (3e-5 at 1024^2 x 820 steps 1st order, measured 3.7e-6; 1e-4 at 256^2 x 1639 steps 2nd order, measured 3.05e-5 = the reference's own FMA-contraction sensitivity); bitwise independent of the "
                    "GPU count, tile and chunk geometry")
 STRICT_ARITH_NOTE = "strict: bit-exact vs the reference C path (FP32 + the reference's two double-promoted expressions per cell)"
 MIN_REGION_S = 0.2     # every reported rate comes from >= this much device time (repetitions of the K-step region, median)

@@ -109,3 +109,17 @@ def test_fast_tolerance_is_anchored_to_the_reference_sensitivity(case, manifest,
     tol = FAST_TOL.get(case, FAST_TOL_DEFAULT)
     assert tol >= 2.0 * sens, f"{case}: tolerance {tol:g} is tighter than 2x the reference's own FMA sensitivity {sens:.2e}"
     assert tol <= max(FAST_TOL_DEFAULT, 5.0 * sens), f"{case}: tolerance {tol:g} is looser than 5x the sensitivity {sens:.2e}"
+
+
+def test_long_run_fast_tolerances_are_anchored():
+    """conftest.FAST_TOL_LONG: each entry at least 2x the reference's own FMA-contraction sensitivity on that run (recorded in the
+    fixture by tests/golden/make_golden_long.py) and at most max(3e-5, 5x) of it."""
+    import json
+    from conftest import FAST_TOL_LONG, GOLDEN_DIR
+    meta = json.load(open(os.path.join(GOLDEN_DIR, "MANIFEST_LONG.json")))
+    assert set(meta) == set(FAST_TOL_LONG)
+    for case, tol in FAST_TOL_LONG.items():
+        sens = float(np.load(os.path.join(GOLDEN_DIR, case + ".npz"))["ref_fma"])
+        assert abs(sens - meta[case]["ref_fma_sensitivity"]) < 1e-12
+        assert tol >= 2.0 * sens or tol >= FAST_TOL_DEFAULT, (case, tol, sens)
+        assert tol <= max(FAST_TOL_DEFAULT, 5.0 * sens), (case, tol, sens)
