@@ -59,6 +59,8 @@ struct shll_ctx {
     KernelKey key;
     int ntiles, nchunks;
     CUtensorMap tmap[2];   // 2D TMA kernels: one 3D map {ny, nx+4, 4} per ping-pong buffer
+    CUtensorMap tmap_out[2];  // face-flux kernel: the same tensors with the TMA-store box (60 owned columns x 4 rows x 4 planes)
+    bool tma_store;
     CUtensorMap *tmap_dev; // the same two descriptors in device memory
     cudaGraphExec_t graph; // single-GPU small grids: GRAPH_STEPS consecutive steps captured once (launch-bound regime)
     bool graph_tried;
@@ -135,7 +137,7 @@ void plan_2d(shll_ctx *c, bool no_tma = false)
     // FAST arithmetic, 2 cells per lane: the face-flux accumulate kernel (step2d_acc.cuh); SHLL_ACC=0 keeps the window kernel.
     c->key.acc = c->key.tma && vec == 2 && g.mode == SHLL_MODE_FAST && env_int("SHLL_ACC", 1) != 0;
     c->key.acc_cfg = env_int("SHLL_ACC_CFG", 1);
-    if (c->key.acc_cfg < 0 || c->key.acc_cfg > 4) c->key.acc_cfg = 1;
+    if (c->key.acc_cfg < 0 || c->key.acc_cfg > 7) c->key.acc_cfg = 1;
     const int hl = (g.order + vec - 1) / vec;
     const int useful = (32 - 2 * hl) * vec;
     c->ntiles = (g.ny + useful - 1) / useful;
@@ -154,6 +156,7 @@ void plan_2d(shll_ctx *c, bool no_tma = false)
     }
     if (rpc < 2) rpc = 2;
     int nchunks = (g.nx + rpc - 1) / rpc;
+    if (env_int("SHLL_NCHUNKS", 0) > 0) nchunks = env_int("SHLL_NCHUNKS", 0);  // experiments: chunk count given directly
     if (nchunks < 1) nchunks = 1;
     while (nchunks > 1 && g.nx / nchunks < 2) nchunks--;
     c->nchunks = nchunks;
@@ -183,7 +186,15 @@ int make_tensor_maps(shll_ctx *c)
                                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) return -(int)r - 100;
+        if (c->key.acc) {
+            cuuint32_t obox[3] = {60, 4, 4};
+            r = ((encode_tiled_fn)fn)(&c->tmap_out[b], CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, dims, strides, obox, estr,
+                                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return -(int)r - 200;
+        }
     }
+    c->tma_store = c->key.acc && env_int("SHLL_TMA_STORE", 1) != 0;
     if (env_int("SHLL_TMAP_GLOBAL", 0)) {
         if (cudaMalloc(&c->tmap_dev, 2 * sizeof(CUtensorMap)) != cudaSuccess) return -2;
         if (cudaMemcpy(c->tmap_dev, c->tmap, 2 * sizeof(CUtensorMap), cudaMemcpyHostToDevice) != cudaSuccess) return -3;
@@ -193,7 +204,9 @@ int make_tensor_maps(shll_ctx *c)
     if (c->tma_stages > 16) c->tma_stages = 16;
     const size_t stage_stride = ((size_t)4 * R * (32 * c->key.vec + 4) * 4 + 127) & ~(size_t)127;
     c->tma_smem = (size_t)c->tma_stages * stage_stride + 8 * c->tma_stages;
-    if (c->key.acc && g.order == 2 && c->key.acc_cfg >= 2) c->tma_smem += (c->key.acc_cfg == 4 ? 2048 : 4096) + 16;  // per-warp stash (step2d_acc.cuh)
+    if (c->key.acc && g.order == 2 && (c->key.acc_cfg == 2 || c->key.acc_cfg == 3 || c->key.acc_cfg == 4))
+        c->tma_smem += (c->key.acc_cfg == 4 ? 2048 : 4096) + 16;  // per-warp stash (step2d_acc.cuh)
+    if (c->tma_store) c->tma_smem += 3840 + 128;                   // per-warp store stage (step2d_acc.cuh: ACC_OUT_STAGE_BYTES)
     return 0;
 }
 
@@ -464,6 +477,8 @@ int launch_one_step(shll_ctx *c)
             Step2DTmaParams T;
             T.base = P;
             T.tmap = c->tmap[in];
+            T.tmap_out = c->tmap_out[outb];
+            T.tma_store = c->tma_store ? 1 : 0;
             T.tmap_global = c->tmap_dev ? c->tmap_dev + in : nullptr;
             T.stages = c->tma_stages;
             // consecutive steps of a single-GPU run overlap their launch with the predecessor's tail (step2d_acc.cu)

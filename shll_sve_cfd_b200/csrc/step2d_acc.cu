@@ -19,6 +19,9 @@ static cudaError_t go_o2(int cfg, const Step2DTmaParams &p, dim3 grid, size_t sm
     case 2: return go<2, BC, LIM, 14, 2>(p, grid, smem, s);
     case 3: return go<2, BC, LIM, 16, 2>(p, grid, smem, s);
     case 4: return go<2, BC, LIM, 14, 1>(p, grid, smem, s);
+    case 5: return go<2, BC, LIM, 16, 0>(p, grid, smem, s);
+    case 6: return go<2, BC, LIM, 14, 0>(p, grid, smem, s);
+    case 7: return go<2, BC, LIM, 10, 0>(p, grid, smem, s);
     }
     return cudaErrorInvalidValue;
 }
@@ -27,6 +30,14 @@ cudaError_t launch_step2d_acc(const KernelKey &k, const Step2DTmaParams &p, dim3
 {
     if (k.mode != MODE_FAST || k.vec != 2) return cudaErrorInvalidValue;
     if (k.order == 1) {
+        if (k.acc_cfg == 5) {   // experiments: more resident warps per SM (register cap 112 / 96)
+            if (k.bc == BC_REFLECT) return go<1, BC_REFLECT, LIM_MINMOD, 18, 0>(p, grid, smem, s);
+            return go<1, BC_OUTFLOW, LIM_MINMOD, 18, 0>(p, grid, smem, s);
+        }
+        if (k.acc_cfg == 6) {
+            if (k.bc == BC_REFLECT) return go<1, BC_REFLECT, LIM_MINMOD, 20, 0>(p, grid, smem, s);
+            return go<1, BC_OUTFLOW, LIM_MINMOD, 20, 0>(p, grid, smem, s);
+        }
         if (k.bc == BC_REFLECT) return go<1, BC_REFLECT, LIM_MINMOD, 16, 0>(p, grid, smem, s);
         if (k.bc == BC_OUTFLOW) return go<1, BC_OUTFLOW, LIM_MINMOD, 16, 0>(p, grid, smem, s);
     } else {

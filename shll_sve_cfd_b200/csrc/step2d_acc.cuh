@@ -111,6 +111,9 @@ struct AccRows {   // warp-uniform row bookkeeping
     int noslope_lo, noslope_hi;    // rows strictly between them get limited x slopes
     float quarter, nquarter;       // 0.25f / -0.25f from kernel parameters: registers, so the sign transfer is one LOP3
     uint32_t stash;                // STASH: shared address of this lane's slot in the 2-row stash of (state - y update)
+    uint32_t sstage_base;          // TMA store: shared address of the warp's store stage (128-byte aligned)
+    uint32_t sstage;               //            ... of this lane's cell pair in row 0, plane 0 of it
+    bool stager;                   //            this lane owns columns of the tile (lanes 1..30)
 };
 
 // Order 2 keeps `state minus y update` of rows r-1 and r-2 until their x update completes.  With STASH these 16 registers
@@ -126,6 +129,20 @@ __device__ __forceinline__ v2 stash_load(uint32_t a)
 __device__ __forceinline__ void stash_store(uint32_t a, v2 v)
 {
     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(a), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// Store stage of a warp: the 4 rows an interior box finishes, dense as the TMA store box wants them --
+// [4 planes][4 rows][60 columns] floats.  Lane l (1..30) owns columns 2(l-1), 2(l-1)+1: conflict-free STS.64 at constant
+// offsets, no address arithmetic, no bounds predicate (the TMA unit clips the ragged last tile).
+constexpr uint32_t ACC_OUT_COLS = 60, ACC_OUT_ROW_BYTES = ACC_OUT_COLS * 4, ACC_OUT_PLANE_BYTES = 4 * ACC_OUT_ROW_BYTES;
+constexpr uint32_t ACC_OUT_STAGE_BYTES = 4 * ACC_OUT_PLANE_BYTES;  // 3840
+template <int WOUT>
+__device__ __forceinline__ void acc_stage_row(const AccRows &W, const v2 (&o)[4])
+{
+    if (W.stager) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) stash_store(W.sstage + k * ACC_OUT_PLANE_BYTES + WOUT * ACC_OUT_ROW_BYTES, o[k]);
+    }
 }
 
 // Split fluxes of row r and its state minus the y-direction update (accN).
@@ -216,7 +233,8 @@ __device__ __forceinline__ void acc_store_owned(const Ctx &X, int i, const v2 (&
 }
 
 // One step of the march: row r arrives, row r-ORDER leaves.  EDGE = this box may contain a physical x wall.
-template <int ORDER, int BC, int LIM, bool WALLTILE, bool EDGE, int STASH, class Ctx>
+// WOUT >= 0: the finished row is row WOUT of the box being staged for a TMA store; -1: plain STG.64.
+template <int ORDER, int BC, int LIM, bool WALLTILE, bool EDGE, int STASH, int WOUT, class Ctx>
 __device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState<ORDER> &S, int r, float (&uin)[2][4])
 {
     const Step2DParams &P = *X.P;
@@ -231,7 +249,9 @@ __device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState
         }
 #pragma unroll
         for (int k = 0; k < 4; k++) o[k] = v2fma(mdtdx, v2sub(S.D[k], g[k]), S.accB[k]);  // Right of row r-1 = F-[r] = -G[r]
-        if (EDGE) { if (r - 1 >= W.r0) acc_store(X, r - 1, o); } else acc_store_owned(X, r - 1, o);
+        if (EDGE) { if (r - 1 >= W.r0) acc_store(X, r - 1, o); }
+        else if (WOUT >= 0) acc_stage_row<(WOUT >= 0 ? WOUT : 0)>(W, o);
+        else acc_store_owned(X, r - 1, o);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             S.D[k] = v2add(v2sub(fp[k], S.fpP[k]), g[k]);
@@ -298,7 +318,9 @@ __device__ __forceinline__ void acc_row(const Ctx &X, const AccRows &W, AccState
             const v2 yB = STASH ? stash_load(slot + k * 256) : S.accB[k];
             o[k] = v2fma(mdtdx, v2sub(S.D[k], gam[k]), yB);  // Right of row r-2 = Phi-[r-1] = -Gamma[r-1]
         }
-        if (EDGE) { if (r - 2 >= W.r0) acc_store(X, r - 2, o); } else acc_store_owned(X, r - 2, o);
+        if (EDGE) { if (r - 2 >= W.r0) acc_store(X, r - 2, o); }
+        else if (WOUT >= 0) acc_stage_row<(WOUT >= 0 ? WOUT : 0)>(W, o);
+        else acc_store_owned(X, r - 2, o);
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             S.D[k] = v2add(v2sub(php[k], S.PhiP[k]), gam[k]);
@@ -325,8 +347,8 @@ __device__ __forceinline__ void acc_read_row(const Ctx &X, int stage, int within
         asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(u[0][k]), "=f"(u[1][k]) : "r"(a + k * Ctx::PLANE_BYTES));
 }
 
-template <int ORDER, int BC, int LIM, bool WALLTILE, int STASH, class Ctx>
-__device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, int rlast, int lane)
+template <int ORDER, int BC, int LIM, bool WALLTILE, int STASH, bool TSTORE, class Ctx>
+__device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, int rlast, int lane, int tile)
 {
     AccState<ORDER> S;
 #pragma unroll
@@ -336,6 +358,7 @@ __device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, in
     uint32_t parity = 0;
     float uin[2][4];
     const int nx = X.P->nx;
+    bool store_pending = false;  // lane 0 has a TMA store in flight that may still be reading the store stage
     for (int box = 0; box < X.nboxes; box++) {
         const int r = rbeg + 4 * box;
         mbar_wait(X.bars + 8u * stage, parity);
@@ -343,30 +366,44 @@ __device__ __forceinline__ void acc_march(Ctx &X, const AccRows &W, int rbeg, in
         // ... or if one of the rows it finishes is not stored by this warp / is also stored into a neighbour GPU's halo
         const int ifirst = r - ORDER;  // rows finished by this box: ifirst .. ifirst + 3
         const bool edge = (r <= 1 && X.P->lo_wall) || (r + 3 >= nx - 1 && X.P->hi_wall) || (r + 3 > rlast) || (ifirst < W.r0) ||
-                          (ifirst < X.peer_lo_end) || (ifirst + 3 >= X.peer_hi_begin);
+                          (ifirst + 3 >= W.r1) || (ifirst < X.peer_lo_end) || (ifirst + 3 >= X.peer_hi_begin);
         if (edge) {
 #pragma unroll 1
             for (int w = 0; w < 4; w++) {
                 if (r + w > rlast) break;
                 acc_read_row(X, stage, w, uin);
-                acc_row<ORDER, BC, LIM, WALLTILE, true, STASH>(X, W, S, r + w, uin);
+                acc_row<ORDER, BC, LIM, WALLTILE, true, STASH, -1>(X, W, S, r + w, uin);
             }
+            __syncwarp();
+            if (lane == 0 && box + X.stages < X.nboxes) X.arm(box + X.stages, stage);
         } else {
+            if (TSTORE) {  // the previous box's TMA store must have finished READING the store stage before it is overwritten
+                if (store_pending) {
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
+            }
             X.template read_row<0>(stage, uin);
-            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH, TSTORE ? 0 : -1>(X, W, S, r, uin);
             X.template read_row<1>(stage, uin);
-            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r + 1, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH, TSTORE ? 1 : -1>(X, W, S, r + 1, uin);
             X.template read_row<2>(stage, uin);
-            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r + 2, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH, TSTORE ? 2 : -1>(X, W, S, r + 2, uin);
             X.template read_row<3>(stage, uin);
-            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH>(X, W, S, r + 3, uin);
+            acc_row<ORDER, BC, LIM, WALLTILE, false, STASH, TSTORE ? 3 : -1>(X, W, S, r + 3, uin);
+            if (TSTORE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // this lane's STS -> visible to the TMA unit
+            // the box has been fully read (and its results staged): store them, refill the ring stage
+            __syncwarp();
+            if (lane == 0) {
+                if (TSTORE) tma_store_3d(&X.T->tmap_out, tile * (int)ACC_OUT_COLS, ifirst + 2, 0, W.sstage_base);
+                if (box + X.stages < X.nboxes) X.arm(box + X.stages, stage);
+            }
+            store_pending = TSTORE;
         }
-        // the box has been fully read: refill its stage, move on
-        __syncwarp();
-        if (lane == 0 && box + X.stages < X.nboxes) X.arm(box + X.stages, stage);
         stage++;
         if (stage == X.stages) { stage = 0; parity ^= 1u; }
     }
+    if (TSTORE && lane == 0) tma_store_wait_all();  // shared memory may not be released under a store that is still reading it
 }
 
 // MINB = resident warps per SM the register allocation is capped for (launch bounds); STASH see above.
@@ -432,10 +469,16 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
     X.lane_off = (uint32_t)(xs - X.x0 + lane * VEC) * 4u;
     X.ybase = rbeg + 2;
     X.nboxes = (rlast - rbeg) / R + 1;
+    uint32_t smem_top = X.bars + 8u * X.stages;
     if (STASH) {  // the host adds 2 KB (level 1) / 4 KB (level 2) + 16 bytes to the dynamic shared memory
-        W.stash = ((X.bars + 8u * X.stages + 15u) & ~15u) + 8u * lane;
+        W.stash = ((smem_top + 15u) & ~15u) + 8u * lane;
         for (int i = 0; i < (STASH >= 2 ? 16 : 8); i++) stash_store(W.stash + i * 256, v2bc(0.0f));
+        smem_top = ((smem_top + 15u) & ~15u) + (STASH >= 2 ? 4096u : 2048u);
     }
+    // store stage (the host adds ACC_OUT_STAGE_BYTES + 128 when T.tma_store is set)
+    W.sstage_base = (smem_top + 127u) & ~127u;
+    W.sstage = W.sstage_base + 8u * (uint32_t)(lane - HL);
+    W.stager = (lane >= HL) && (lane < 32 - HL);
     if (lane == 0) {
         for (int s = 0; s < X.stages; s++) mbar_init(X.bars + 8u * s, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -447,8 +490,9 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
     }
     __syncwarp();
 
-    if (X.Y.tile_has_wall) acc_march<ORDER, BC, LIM, true, STASH>(X, W, rbeg, rlast, lane);
-    else acc_march<ORDER, BC, LIM, false, STASH>(X, W, rbeg, rlast, lane);
+    if (X.Y.tile_has_wall) acc_march<ORDER, BC, LIM, true, STASH, false>(X, W, rbeg, rlast, lane, tile);  // (few tiles: keep one code path)
+    else if (T.tma_store) acc_march<ORDER, BC, LIM, false, STASH, true>(X, W, rbeg, rlast, lane, tile);
+    else acc_march<ORDER, BC, LIM, false, STASH, false>(X, W, rbeg, rlast, lane, tile);
 
     if (P.sync.enabled) {
         if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);

@@ -28,6 +28,8 @@ namespace shll {
 struct Step2DTmaParams {
     Step2DParams base;
     CUtensorMap tmap;     // INPUT buffer as a 3D tensor {ny, nx+4, 4 planes}, origin = halo row -2 of plane 0
+    CUtensorMap tmap_out; // step2d_acc.cuh: OUTPUT buffer, same tensor, box = 60 owned columns x 4 rows x 4 planes (TMA store)
+    int tma_store;        // step2d_acc.cuh: interior boxes leave through one cp.async.bulk.tensor store per box
     const CUtensorMap *tmap_global;  // optional copy of the same descriptor in device memory (debug switch SHLL_TMAP_GLOBAL)
     int stages;
     int pdl;              // launched with programmatic stream serialization: the kernel waits for its predecessor itself (halo_sync.cuh)
@@ -64,6 +66,17 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
         : "memory");
 }
+
+// TMA store: shared -> global, tracked by the issuing thread's bulk async-groups.
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, int x, int y, int z, uint32_t src)
+{
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(map), "r"(x), "r"(y), "r"(z),
+                 "r"(src)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // Row source + store sink of one warp for the TMA kernel.
 template <int VEC, int R>
