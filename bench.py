@@ -496,8 +496,20 @@ def measure(h, workload, mode_name, K, W, want_e2e, want_parity, sampler_gpu=Non
     if sampler is not None:
         sampler.wait_first()
     l0 = s.launches
+    hw0 = s.halo_wait_stats() if h.world > 1 else None
     ms, clocks, reps = timed_reps(h, s, K, sampler)
     launches = (s.launches - l0) // (reps + 1)
+    halo = None
+    if h.world > 1:   # attribution of the scaling loss: time the edge warps spent spinning on a neighbour's flag, per rank
+        hw1 = s.halo_wait_stats()
+        mine = {"rank": h.rank, "lower_us_per_step": (hw1["lower_s"] - hw0["lower_s"]) * 1e6 / (K * (reps + 1)),
+                "upper_us_per_step": (hw1["upper_s"] - hw0["upper_s"]) * 1e6 / (K * (reps + 1)), "waits": hw1["waits"] - hw0["waits"]}
+        allr = [None] * h.world
+        h.dist.all_gather_object(allr, mine)
+        halo = {"halo_steps_per_exchange": getattr(ss, "halo_steps", 1),
+                "edge_warp_wait_us_per_step_max_over_ranks": max(max(r["lower_us_per_step"], r["upper_us_per_step"]) for r in allr),
+                "edge_warp_wait_us_per_step_per_rank": [[round(r["lower_us_per_step"], 3), round(r["upper_us_per_step"], 3)] for r in allr],
+                "note": "summed over the edge warps of a step (2D: one per column tile and side), not wall time: interior warps never wait"}
     if sampler is not None:
         sampler.stop()
     med = float(np.median(ms))
@@ -506,7 +518,7 @@ def measure(h, workload, mode_name, K, W, want_e2e, want_parity, sampler_gpu=Non
     r = dict(pb=pb, nloc=nloc, total_cells=total_cells, ncomp=ncomp, ms=med, ms_min=float(min(ms)), ms_max=float(max(ms)), reps=reps,
              region_s=float(sum(ms)) * 1e-3, launches=launches, variant=s.variant, clocks=clocks, grid_per_gpu=[ss.slab.nx_local, ny_],
              value=total_cells * K / (med * 1e-3), achieved=bytes_per_launch * K / (med * 1e-3) / 1e9, peak=peak, peak_src=peak_src,
-             bytes_per_launch=bytes_per_launch)
+             bytes_per_launch=bytes_per_launch, halo=halo)
     if want_e2e:
         # end to end through the C ABI with host buffers: upload + K steps + download inside the timed region
         host_out = torch.empty((ncomp, nloc), dtype=torch.float32, pin_memory=True)
@@ -550,7 +562,7 @@ def workload_block(h, name, r, K):
             "ms_per_step_min_max": [r["ms_min"] / K, r["ms_max"] / K],
             "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s", "frac": r["achieved"] / r["peak"],
                          "traffic": tr, "traffic_source": tr_src, "algorithmic_bytes_per_step": r["bytes_per_launch"]},
-            "clocks": r["clocks"], "parity_vs_1gpu": r.get("parity_vs_1gpu"), **per_launch_note}
+            "clocks": r["clocks"], "parity_vs_1gpu": r.get("parity_vs_1gpu"), "halo_exchange": r.get("halo"), **per_launch_note}
 
 
 def main():
@@ -635,6 +647,7 @@ def main():
                          "algorithmic_bytes_per_launch": r["bytes_per_launch"], "kernel": r["variant"]},
             "clocks": r["clocks"],
             "parity_vs_1gpu": r.get("parity_vs_1gpu"),
+            "halo_exchange": r.get("halo"),
             "workloads": blocks,
         }
         if "checksum" in r:

@@ -84,7 +84,11 @@ typedef struct shll_config {
     int32_t rank;          /* slab index along x, 0 .. nranks-1 */
     int32_t nranks;        /* number of slabs; slab 0 owns the x=0 wall, slab nranks-1 the x=NX-1 wall */
     int32_t variant;       /* kernel variant: 0 = auto; otherwise a tuning id */
-    int32_t reserved[7];
+    int32_t halo_steps;    /* 1D slabs (nranks > 1): time steps per halo exchange round, K.  Neighbouring GPUs exchange
+                              K*order cells once every K steps instead of `order` cells every step (temporal blocking; same
+                              bits).  Must be the same on every slab, K*order <= 32 and <= the smallest slab.  0 = 1 (exchange
+                              every step); shll_group_create and the Python slab front end choose it from the whole domain */
+    int32_t reserved[6];
 } shll_config;
 
 typedef struct shll_ctx shll_ctx;
@@ -127,6 +131,10 @@ SHLL_API int shll_max_cfl(shll_ctx *ctx, float *cfl);
  * (reproducible run to run).  With reflective walls (base_shll.c:93-110) mass and energy are conserved by the scheme up
  * to FP32 rounding of the update; multi-GPU callers add the per-slab sums. */
 SHLL_API int shll_conserved_sums(shll_ctx *ctx, double sums[4]);
+
+/* Multi-GPU attribution: time the edge warps of this context spent spinning on a neighbour's halo flag since creation.
+ * stats[0] = seconds waiting for the lower neighbour, [1] = for the upper neighbour, [2] = number of waits that had to spin. */
+SHLL_API int shll_halo_wait_stats(shll_ctx *ctx, double stats[3]);
 
 /* Number of kernels this context has launched so far (bench.py's gpu_launches). */
 SHLL_API long shll_launch_count(const shll_ctx *ctx);

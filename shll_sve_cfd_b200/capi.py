@@ -22,7 +22,7 @@ API_SYMBOLS = [
     "shll_abi_version", "shll_last_error", "shll_count_steps", "shll_create", "shll_destroy", "shll_upload_u",
     "shll_download_u", "shll_download_p", "shll_run", "shll_sync", "shll_run_timed", "shll_max_cfl",
     "shll_conserved_sums", "shll_selftest_exact_division",
-    "shll_launch_count", "shll_variant_name", "shll_peer_export", "shll_peer_connect",
+    "shll_halo_wait_stats", "shll_launch_count", "shll_variant_name", "shll_peer_export", "shll_peer_connect",
     "shll_group_create", "shll_group_destroy", "shll_group_last_error", "shll_group_size", "shll_group_ctx",
     "shll_group_upload_u", "shll_group_download_u", "shll_group_download_p", "shll_group_run", "shll_group_run_timed",
     "shll_group_max_cfl", "shll_group_conserved_sums", "shll_group_launch_count",
@@ -34,8 +34,8 @@ class Config(C.Structure):
         ("struct_size", C.c_uint32), ("dims", C.c_int32), ("nx", C.c_int32), ("ny", C.c_int32),
         ("order", C.c_int32), ("bc", C.c_int32), ("limiter", C.c_int32), ("tform", C.c_int32), ("mode", C.c_int32),
         ("alpha", C.c_float), ("dt_on_dx", C.c_float), ("dt_on_dy", C.c_float),
-        ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("variant", C.c_int32),
-        ("reserved", C.c_int32 * 7),
+        ("device", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32), ("variant", C.c_int32), ("halo_steps", C.c_int32),
+        ("reserved", C.c_int32 * 6),
     ]
 
 
@@ -81,6 +81,7 @@ def lib():
         L.shll_run_timed.argtypes = [C.c_void_p, C.c_long, C.POINTER(C.c_float)]
         L.shll_max_cfl.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
         L.shll_conserved_sums.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.shll_halo_wait_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.shll_selftest_exact_division.argtypes = [C.c_int, C.c_ulonglong, C.c_ulonglong, C.POINTER(C.c_ulonglong)]
         L.shll_launch_count.restype = C.c_long
         L.shll_launch_count.argtypes = [C.c_void_p]
@@ -139,13 +140,14 @@ class Solver:
     """One slab on one GPU.  Mirrors the C usage: create -> upload_u -> run(nsteps) -> download_u/p -> destroy."""
 
     def __init__(self, dims, nx, ny=1, order=1, bc=BC_REFLECT, limiter=LIM_MINMOD, tform=TFORM_AUTO,
-                 mode=MODE_STRICT, alpha=1.25, dt_on_dx=0.125, dt_on_dy=0.125, device=0, rank=0, nranks=1, variant=0):
+                 mode=MODE_STRICT, alpha=1.25, dt_on_dx=0.125, dt_on_dy=0.125, device=0, rank=0, nranks=1, variant=0, halo_steps=0):
         self.cfg = Config()
         self.cfg.struct_size = C.sizeof(Config)
         self.cfg.dims, self.cfg.nx, self.cfg.ny = dims, nx, (ny if dims == 2 else 1)
         self.cfg.order, self.cfg.bc, self.cfg.limiter, self.cfg.tform, self.cfg.mode = order, bc, limiter, tform, mode
         self.cfg.alpha, self.cfg.dt_on_dx, self.cfg.dt_on_dy = alpha, dt_on_dx, dt_on_dy
         self.cfg.device, self.cfg.rank, self.cfg.nranks, self.cfg.variant = device, rank, nranks, variant
+        self.cfg.halo_steps = halo_steps
         self.ncomp = 3 if dims == 1 else 4
         self.ncells = nx * (ny if dims == 2 else 1)
         self._h = C.c_void_p(None)
@@ -195,6 +197,12 @@ class Solver:
         v = (C.c_double * 4)()
         self._ck(lib().shll_conserved_sums(self._h, v))
         return np.array(v[:], dtype=np.float64)
+
+    def halo_wait_stats(self) -> dict:
+        """Seconds the edge warps spent spinning on the neighbours' halo flags since creation (multi-GPU attribution)."""
+        v = (C.c_double * 3)()
+        self._ck(lib().shll_halo_wait_stats(self._h, v))
+        return {"lower_s": v[0], "upper_s": v[1], "waits": int(v[2])}
 
     @property
     def launches(self) -> int:

@@ -36,6 +36,7 @@ struct HaloSync {
     unsigned edge_warps_hi;
     unsigned *err;             // local error word (0 = ok)
     unsigned long long timeout_ns;
+    unsigned long long *wait_ns;  // local statistics: [0] ns spent spinning on the lower flag, [1] upper, [2] number of waits that spun
 };
 
 __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p)
@@ -60,7 +61,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 // already enqueued behind it -- returns at once, so a lost neighbour costs ONE timeout, not one per edge warp per step.
 // The halo rows come from the peer GPU through the generic proxy; the TMA kernels read them through the async proxy, so
 // the acquire is followed by a proxy fence (edge warps only: 2*ntiles warps per step).
-__device__ __forceinline__ void halo_wait(const HaloSync &S, const unsigned *flag)
+__device__ __forceinline__ void halo_wait(const HaloSync &S, const unsigned *flag, int side = 0)
 {
     if (flag == nullptr) return;
     if ((threadIdx.x & 31) == 0) {
@@ -76,6 +77,10 @@ __device__ __forceinline__ void halo_wait(const HaloSync &S, const unsigned *fla
                         break;
                     }
                 }
+            }
+            if (S.wait_ns != nullptr) {  // attribution of what is left of the scaling loss (bench.py: halo_wait_us_per_step)
+                atomicAdd(S.wait_ns + side, globaltimer_ns() - t0);
+                atomicAdd(S.wait_ns + 2, 1ull);
             }
         }
         asm volatile("fence.proxy.async;" ::: "memory");

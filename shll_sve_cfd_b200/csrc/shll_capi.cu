@@ -26,7 +26,13 @@ using namespace shll;
 namespace {
 
 constexpr int HALO_ROWS = 2;
-constexpr int FLAG_WORDS = 64;  // [0]=arrived from lower, [1]=arrived from upper, [2]=cnt_lo, [3]=cnt_hi, [4]=err, [8]=cfl
+// [0]=arrived from lower, [1]=arrived from upper, [2]=cnt_lo, [3]=cnt_hi, [4]=err, [8]=cfl, [16..21]=halo-wait statistics (3 x u64),
+// [MAIL_OFF ..) = 1D halo mailboxes [side: 0 = filled by the lower neighbour, 1 = by the upper][round parity][3 comps][HALO1D_MAX]
+constexpr int FLAG_WORDS = 1024;
+constexpr int MAIL_OFF = 128;
+constexpr int WAIT_STATS_OFF = 16;
+
+inline size_t mail_index(int side, unsigned round, int k) { return MAIL_OFF + (size_t)(((side * 2 + (int)(round & 1u)) * 3 + k) * HALO1D_MAX); }
 
 thread_local char g_create_error[512] = "";
 
@@ -56,6 +62,11 @@ struct shll_ctx {
     long launches;
     unsigned state_index;  // time steps taken since creation (monotonic; halo flags are expressed in it)
     unsigned epoch;        // step launches since creation
+    // 1D slabs: temporal blocking of the halo exchange (step1d.cuh)
+    int halo_K;            // steps per exchange round (1 = exchange every step)
+    unsigned round;        // exchange rounds completed since creation (monotonic; the 1D halo flags are expressed in it)
+    unsigned sends;        // send steps launched since creation
+    unsigned origin;       // state_index at the last upload: rounds restart there
     KernelKey key;
     int ntiles, nchunks;
     CUtensorMap tmap[2];   // 2D TMA kernels: one 3D map {ny, nx+4, 4} per ping-pong buffer
@@ -263,6 +274,10 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     if (g.tform == SHLL_TFORM_AUTO) g.tform = (g.dims == 1 && g.order == 1) ? SHLL_TFORM_1D : SHLL_TFORM_2D;
     if (g.dims == 2) g.tform = SHLL_TFORM_2D;
     if (!(g.dt_on_dx > 0.0f) || (g.dims == 2 && !(g.dt_on_dy > 0.0f))) return fail(nullptr, SHLL_E_INVAL, "dt_on_dx / dt_on_dy must be positive");
+    if (g.halo_steps <= 0 || g.dims != 1 || g.nranks == 1) g.halo_steps = 1;
+    if (g.halo_steps * g.order > HALO1D_MAX || g.halo_steps * g.order > g.nx)
+        return fail(nullptr, SHLL_E_INVAL, "halo_steps = %d: %d halo cells per side exceed the limit of %d or the slab's %d cells", g.halo_steps,
+                    g.halo_steps * g.order, HALO1D_MAX, g.nx);
 
     if ((double)(g.nx + 8) * (double)g.ny >= 2147483647.0)
         return fail(nullptr, SHLL_E_INVAL, "slab of %d x %d cells exceeds the 32-bit plane index used by the kernels; use more slabs", g.nx, g.ny);
@@ -287,6 +302,7 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
         c->interior_off = (size_t)HALO_ROWS * g.ny;
         c->plane_elems = round_up((size_t)(g.nx + 2 * HALO_ROWS) * g.ny, 64);
     }
+    c->halo_K = g.halo_steps;
     c->key.order = g.order;
     c->key.bc = g.bc;
     c->key.lim = g.limiter;
@@ -452,7 +468,9 @@ int launch_one_step(shll_ctx *c)
         S.cnt_hi = c->flags + 3;
         S.err = c->flags + 4;
         S.timeout_ns = (unsigned long long)env_int("SHLL_HALO_TIMEOUT_MS", 5000) * 1000000ull;
+        S.wait_ns = reinterpret_cast<unsigned long long *>(c->flags + WAIT_STATS_OFF);
     }
+    bool sent = false;
     cudaError_t e;
     if (g.dims == 2) {
         Step2DParams P;
@@ -497,35 +515,60 @@ int launch_one_step(shll_ctx *c)
     } else {
         Step1DParams P;
         memset(&P, 0, sizeof(P));
+        // Slabs: temporal blocking of the halo exchange (step1d.cuh).  Position of this step in its round of K steps:
+        const bool m = multi(c);
+        const int K = m ? c->halo_K : 1, H = K * g.order;
+        const int pos = m ? (int)((c->state_index - c->origin) % (unsigned)K) : 0;
+        const bool recv = m && pos == 0, send = m && pos == K - 1;
+        const int ext = (!m || send) ? 0 : (int)round_up((size_t)(H - g.order * (pos + 1)), 4);  // halo cells this step still updates
+        const int ext_lo = lo_wall ? 0 : ext, ext_hi = hi_wall ? 0 : ext;
         for (int k = 0; k < 3; k++) {
-            P.in[k] = c->plane(in, k);
-            P.out[k] = c->plane(outb, k);
-            P.lo_peer[k] = (multi(c) && !lo_wall) ? peer_halo_ptr(c, 0, outb, k) : nullptr;
-            P.hi_peer[k] = (multi(c) && !hi_wall) ? peer_halo_ptr(c, 1, outb, k) : nullptr;
+            P.in[k] = c->plane(in, k) - ext_lo;
+            P.out[k] = c->plane(outb, k) - ext_lo;
+            // destination = the neighbours' mailboxes of the round that CONSUMES this data (round + 1)
+            P.lo_peer[k] = (send && !lo_wall) ? reinterpret_cast<float *>(c->peer_flags[0] + mail_index(1, c->round + 1, k)) : nullptr;
+            P.hi_peer[k] = (send && !hi_wall) ? reinterpret_cast<float *>(c->peer_flags[1] + mail_index(0, c->round + 1, k)) : nullptr;
         }
-        P.n = g.nx;
+        P.n = g.nx + ext_lo + ext_hi;
+        P.n_real = g.nx;
+        P.ext_lo = ext_lo;
+        P.recv = recv ? 1 : 0;
+        P.xch = send ? H : 0;
+        P.hcells = H;
+        P.mail_lo = (recv && !lo_wall) ? reinterpret_cast<const float *>(c->flags + mail_index(0, c->round, 0)) : nullptr;
+        P.mail_hi = (recv && !hi_wall) ? reinterpret_cast<const float *>(c->flags + mail_index(1, c->round, 0)) : nullptr;
+        P.interior_end = P.n;
+        if (recv && !hi_wall && ext_lo + g.nx < P.interior_end) P.interior_end = ext_lo + g.nx;  // tiles reading the upper halo cells
+        if (send && !hi_wall && g.nx - H < P.interior_end) P.interior_end = g.nx - H;           // tiles owning cells to be sent
         P.lo_wall = lo_wall; P.hi_wall = hi_wall;
-        P.ntiles = c->ntiles;
+        P.ntiles = (P.n + 119) / 120;
         P.dtdx = g.dt_on_dx; P.half_dtdx = 0.5f * g.dt_on_dx; P.alpha = g.alpha;
         P.quarter = 0.25f;
         // 4 (face-flux kernel: 8) consecutive tiles per warp on large tubes (B200 sweep: profiles/); small tubes keep one warp
         // per tile so that all SMs work
         const int tpw_big = c->key.acc ? 8 : 4;
-        P.tiles_per_warp = env_int("SHLL_1D_TILES_PER_WARP", c->ntiles >= tpw_big * 4096 ? tpw_big : (c->ntiles >= 4096 ? c->ntiles / 4096 : 1));
+        P.tiles_per_warp = env_int("SHLL_1D_TILES_PER_WARP", P.ntiles >= tpw_big * 4096 ? tpw_big : (P.ntiles >= 4096 ? P.ntiles / 4096 : 1));
         if (P.tiles_per_warp < 1) P.tiles_per_warp = 1;
-        S.edge_warps_lo = 1;
-        S.edge_warps_hi = (unsigned)((g.nx - 1) / 120 - (g.nx - g.order) / 120 + 1);
+        if (m) {  // the 1D flags count exchange ROUNDS, the arrival counters count send steps
+            S.want = c->round + 1;
+            S.post = c->round + 2;
+            S.epoch = c->sends + 1;
+            S.edge_warps_lo = 1;
+            S.edge_warps_hi = (unsigned)((g.nx - 1) / 120 - (g.nx - H) / 120 + 1);
+        }
         P.sync = S;
         P.pdl = use_pdl(c);
-        const int warps = (c->ntiles + P.tiles_per_warp - 1) / P.tiles_per_warp;  // a warp marches through consecutive tiles
+        const int warps = (P.ntiles + P.tiles_per_warp - 1) / P.tiles_per_warp;  // a warp marches through consecutive tiles
         dim3 block(128), grid((warps + 3) / 4);
         e = launch_step1d(c->key, P, grid, block, c->stream);
+        sent = send;
     }
     if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "step kernel launch failed (%s): %s", c->variant, cudaGetErrorString(e));
     c->cur = outb;
     c->state_index++;
     c->epoch++;
     c->launches++;
+    if (sent) { c->round++; c->sends++; }
     return SHLL_OK;
 }
 
@@ -620,7 +663,18 @@ int shll_upload_u(shll_ctx *c, const float *const u[4])
         // publish our edge rows of the freshly uploaded state to the neighbours' halos
         const shll_config &g = c->cfg;
         const bool lo_wall = (g.rank == 0), hi_wall = (g.rank == g.nranks - 1);
-        const long row = g.dims == 1 ? 1 : g.ny;
+        if (g.dims == 1) {
+            // 1D: a new exchange round starts at this state; the outermost H = K*order cells go into the neighbours' mailboxes
+            const long H = (long)c->halo_K * g.order;
+            c->origin = c->state_index;
+            push_halo_kernel<<<1, 128, 0, c->stream>>>(c->plane(c->cur, 0), c->plane(c->cur, 0) + (g.nx - H),
+                                                        lo_wall ? nullptr : reinterpret_cast<float *>(c->peer_flags[0] + mail_index(1, c->round, 0)),
+                                                        hi_wall ? nullptr : reinterpret_cast<float *>(c->peer_flags[1] + mail_index(0, c->round, 0)),
+                                                        H, c->ncomp, c->plane_elems, HALO1D_MAX, HALO1D_MAX,
+                                                        lo_wall ? nullptr : c->peer_flags[0] + 1, hi_wall ? nullptr : c->peer_flags[1] + 0,
+                                                        c->round + 1);
+        } else {
+        const long row = g.ny;
         const long count = (long)g.order * row;
         const float *src_lo = c->plane(c->cur, 0);
         const float *src_hi = c->plane(c->cur, 0) + ((long)g.nx - g.order) * row;
@@ -631,6 +685,7 @@ int shll_upload_u(shll_ctx *c, const float *const u[4])
                                                      hi_wall ? 0 : peer_plane_elems(c->peer_desc[1]),
                                                      lo_wall ? nullptr : c->peer_flags[0] + 1,
                                                      hi_wall ? nullptr : c->peer_flags[1] + 0, c->state_index + 1);
+        }
         CK(c, cudaGetLastError());
         c->launches++;
     }
@@ -789,6 +844,19 @@ int shll_conserved_sums(shll_ctx *c, double sums[4])
         for (int b = 0; b < nb; b++) t += host[(size_t)b * 4 + k];
         sums[k] = (k < c->ncomp) ? t : 0.0;
     }
+    return SHLL_OK;
+}
+
+int shll_halo_wait_stats(shll_ctx *c, double stats[3])
+{
+    if (!c || !stats) return fail(c, SHLL_E_INVAL, "shll_halo_wait_stats: null argument");
+    CK(c, cudaSetDevice(c->cfg.device));
+    unsigned long long raw[3] = {0, 0, 0};
+    CK(c, cudaMemcpyAsync(raw, c->flags + WAIT_STATS_OFF, sizeof(raw), cudaMemcpyDeviceToHost, c->stream));
+    CK(c, cudaStreamSynchronize(c->stream));
+    stats[0] = (double)raw[0] * 1e-9;
+    stats[1] = (double)raw[1] * 1e-9;
+    stats[2] = (double)raw[2];
     return SHLL_OK;
 }
 

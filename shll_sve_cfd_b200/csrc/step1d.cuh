@@ -15,7 +15,10 @@
 
 namespace shll {
 
-constexpr int PAD1D = 4;
+// Padding on both sides of a 1D plane: HALO1D_MAX halo cells of a slab (temporal blocking of the GPU-to-GPU exchange, see below)
+// + the 4 cells of lane 0's float4 + 4 spare.  A multiple of 4 floats, so owned cell 0 stays 16-byte aligned.
+constexpr int HALO1D_MAX = 32;
+constexpr int PAD1D = HALO1D_MAX + 8;
 
 struct Step1DParams {
     const float *in[3];  // plane base = local cell 0
@@ -29,8 +32,45 @@ struct Step1DParams {
     int tiles_per_warp;  // step1d_acc.cuh: consecutive tiles one warp marches through (register prefetch of the next one)
     float quarter;  // 0.25f as a parameter (register operand of the one-LOP3 sign transfer, step1d_acc.cuh)
     int pdl;        // launched with programmatic stream serialization (halo_sync.cuh: pdl_wait_for_previous_step)
-    HaloSync sync;  // multi-GPU only
+    // ---- multi-GPU slabs: temporal blocking of the halo exchange -------------------------------------------------------
+    // Neighbouring GPUs exchange H = K*ORDER cells once every K steps instead of ORDER cells every step: a round starts with
+    // the H halo cells of both sides valid, every step of the round the kernel ALSO updates the halo cells that are still
+    // valid (the garbage front moves ORDER cells inward per step and reaches cell 0 exactly when the round ends), and the last
+    // step of the round sends the slab's outermost H owned cells to the neighbours' mailboxes.  K-1 of K steps have no
+    // cross-GPU dependency at all.  The host shifts in/out/n so that tile 0 starts at the first cell to be updated:
+    //   in[k], out[k] = plane + real cell -ext_lo ;  n = n_real + ext_lo + ext_hi   (ext = 0 at a wall and on send steps).
+    int recv;            // this step starts a round: edge tiles wait for the neighbours' flags and copy the mailboxes into the halo cells
+    int xch;             // > 0: this step ends a round: send the outermost xch (= H) owned cells of each side (ext_lo == ext_hi == 0)
+    int hcells;          // H
+    int ext_lo, n_real;  // see above
+    int interior_end;    // tiles reaching cell index interior_end - ORDER (shifted coordinates) or beyond take the EDGE path
+    const float *mail_lo, *mail_hi;  // local mailboxes [3][HALO1D_MAX] the neighbours filled (read on recv steps), NULL at a wall
+    HaloSync sync;       // multi-GPU only; lo_peer / hi_peer above point at the NEIGHBOURS' mailboxes (component stride HALO1D_MAX)
 };
+
+// recv step, edge tiles only (whole warp): wait for the neighbour, then copy its mailbox into the halo cells of the input
+// plane.  Several warps may do this for the same side (every tile that reads a halo cell does): they write identical values.
+__device__ __forceinline__ void step1d_recv_halo(const Step1DParams &P, bool lo, bool hi)
+{
+    const int lane = threadIdx.x & 31;
+    if (lo && P.mail_lo != nullptr) {
+        halo_wait(P.sync, P.sync.wait_lo, 0);
+        if (lane < P.hcells) {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                const_cast<float *>(P.in[k])[P.ext_lo - P.hcells + lane] = *(const volatile float *)(P.mail_lo + k * HALO1D_MAX + lane);
+        }
+    }
+    if (hi && P.mail_hi != nullptr) {
+        halo_wait(P.sync, P.sync.wait_hi, 1);
+        if (lane < P.hcells) {
+#pragma unroll
+            for (int k = 0; k < 3; k++)
+                const_cast<float *>(P.in[k])[P.ext_lo + P.n_real + lane] = *(const volatile float *)(P.mail_hi + k * HALO1D_MAX + lane);
+        }
+    }
+    __syncwarp();  // the tile's own loads of those cells come after every lane's stores
+}
 
 // ---- how a warp gets its tiles ------------------------------------------------------------------------------------
 // A warp marches through `tiles_per_warp` consecutive tiles.  Their loads go through a per-warp shared-memory ring filled
@@ -86,7 +126,7 @@ __device__ __forceinline__ void step1d_ring_march(const Step1DParams &P, F &&til
                          : "r"(base + stage * STAGE_BYTES + k * 512u)
                          : "memory");
         // interior tile: all 128 loaded cells and their +-ORDER neighbours are real owned cells of this slab
-        const bool interior = (tile > 0) && ((long)tile * 120 + 124 + order <= (long)P.n - order);
+        const bool interior = (tile > 0) && ((long)tile * 120 + 124 + order <= (long)P.interior_end - order);
         tile_fn(tile, lane, interior, cur);
         if (++stage == STEP1D_STAGES) stage = 0;
     }
@@ -108,11 +148,10 @@ __device__ __forceinline__ void step1d_tile(const Step1DParams &P, int tile, int
     const bool lo_wall = P.lo_wall != 0, hi_wall = P.hi_wall != 0;
     // warps owning one of the first / last ORDER cells exchange halos with the neighbour GPUs
     const int own_lo = tile * USEFUL, own_hi = min(own_lo + USEFUL, n);  // owned cells [own_lo, own_hi)
-    const bool touch_lo = EDGE && (own_lo < ORDER), touch_hi = EDGE && (own_hi > n - ORDER) && (own_lo < n);
-    if (EDGE && P.sync.enabled) {
-        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
-        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
-    }
+    // send step: warps owning one of the outermost xch cells; recv step: warps whose loads reach a halo cell
+    const bool touch_lo = EDGE && (own_lo < P.xch), touch_hi = EDGE && (own_hi > n - P.xch) && (own_lo < n);
+    if (EDGE && P.sync.enabled && P.recv)
+        step1d_recv_halo(P, tile == 0, (long)tile * USEFUL + 124 > (long)P.ext_lo + P.n_real);
 
     float u[VEC][3], fp[VEC][3], fm[VEC][3];
 #pragma unroll
@@ -211,16 +250,16 @@ __device__ __forceinline__ void step1d_tile(const Step1DParams &P, int tile, int
             for (int v = 0; v < VEC; v++)
                 if (j0 + v < n) P.out[k][j0 + v] = uo[v][k];
         }
-        // halo exchange fused into the step: edge cells go straight into the neighbour GPU's halo cells
-        if (P.lo_peer[k] != nullptr && j0 < ORDER) {
+        // halo exchange fused into the step: the outermost xch cells go straight into the neighbour GPU's mailbox
+        if (P.lo_peer[k] != nullptr && j0 < P.xch) {
 #pragma unroll
             for (int v = 0; v < VEC; v++)
-                if (j0 + v < ORDER && j0 + v < n) P.lo_peer[k][j0 + v] = uo[v][k];
+                if (j0 + v < P.xch && j0 + v < n) P.lo_peer[k][j0 + v] = uo[v][k];
         }
-        if (P.hi_peer[k] != nullptr && j0 + VEC > n - ORDER) {
+        if (P.hi_peer[k] != nullptr && j0 + VEC > n - P.xch) {
 #pragma unroll
             for (int v = 0; v < VEC; v++)
-                if (j0 + v >= n - ORDER && j0 + v < n) P.hi_peer[k][j0 + v - (n - ORDER)] = uo[v][k];
+                if (j0 + v >= n - P.xch && j0 + v < n) P.hi_peer[k][j0 + v - (n - P.xch)] = uo[v][k];
         }
     }
     if (P.sync.enabled) {

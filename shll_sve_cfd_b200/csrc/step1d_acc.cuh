@@ -41,18 +41,16 @@ __device__ __forceinline__ void cell_flux_1d_fast_x2g(const v2 (&u)[3], v2 (&fp)
 template <int BC, int LIM, bool EDGE>
 __device__ __forceinline__ void step1d_acc_tile(const Step1DParams &P, int tile, int lane, const float4 (&in)[3])
 {
-    constexpr int VEC = 4, ORDER = 2;
+    constexpr int VEC = 4;
     constexpr int USEFUL = 30 * VEC;
     const unsigned full = 0xffffffffu;
     const int n = P.n;
     const int j0 = tile * USEFUL + (lane - 1) * VEC;
     const bool lo_wall = P.lo_wall != 0, hi_wall = P.hi_wall != 0;
     const int own_lo = tile * USEFUL, own_hi = min(own_lo + USEFUL, n);
-    const bool touch_lo = EDGE && (own_lo < ORDER), touch_hi = EDGE && (own_hi > n - ORDER) && (own_lo < n);
-    if (EDGE && P.sync.enabled) {
-        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
-        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
-    }
+    const bool touch_lo = EDGE && (own_lo < P.xch), touch_hi = EDGE && (own_hi > n - P.xch) && (own_lo < n);
+    if (EDGE && P.sync.enabled && P.recv)
+        step1d_recv_halo(P, tile == 0, (long)tile * USEFUL + 124 > (long)P.ext_lo + P.n_real);
 
     v2 u[2][3], fp[2][3], g[2][3];  // [pair][component]: pair 0 = cells j0, j0+1; pair 1 = cells j0+2, j0+3
 #pragma unroll
@@ -138,15 +136,15 @@ __device__ __forceinline__ void step1d_acc_tile(const Step1DParams &P, int tile,
                 if (j0 + v < n) P.out[k][j0 + v] = o[v];
         }
         // halo exchange fused into the step: edge cells go straight into the neighbour GPU's halo cells
-        if (P.lo_peer[k] != nullptr && j0 < ORDER) {
+        if (P.lo_peer[k] != nullptr && j0 < P.xch) {
 #pragma unroll
             for (int v = 0; v < VEC; v++)
-                if (j0 + v < ORDER && j0 + v < n) P.lo_peer[k][j0 + v] = o[v];
+                if (j0 + v < P.xch && j0 + v < n) P.lo_peer[k][j0 + v] = o[v];
         }
-        if (P.hi_peer[k] != nullptr && j0 + VEC > n - ORDER) {
+        if (P.hi_peer[k] != nullptr && j0 + VEC > n - P.xch) {
 #pragma unroll
             for (int v = 0; v < VEC; v++)
-                if (j0 + v >= n - ORDER && j0 + v < n) P.hi_peer[k][j0 + v - (n - ORDER)] = o[v];
+                if (j0 + v >= n - P.xch && j0 + v < n) P.hi_peer[k][j0 + v - (n - P.xch)] = o[v];
         }
     }
     if (P.sync.enabled) {

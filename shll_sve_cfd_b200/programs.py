@@ -208,12 +208,23 @@ def save_results(pb: Problem, p: np.ndarray, path: str) -> None:
                     c += 1
 
 
+def halo_steps_for(pb: Problem, nranks: int, want: int | None = None) -> int:
+    """K of the 1D temporal halo blocking (include/shll_b200.h: shll_config.halo_steps) for a domain of pb.nx cells cut into
+    nranks balanced slabs: the same value on every rank, K*order <= 32 and <= the smallest slab.  SHLL_HALO_K overrides 16."""
+    import os
+    if pb.dims != 1 or nranks <= 1:
+        return 1
+    k = want if want is not None else int(os.environ.get("SHLL_HALO_K", "16"))
+    smallest = pb.nx // nranks
+    return max(1, min(k, 32 // pb.order, smallest // pb.order))
+
+
 def make_solver(pb: Problem, mode: int = capi.MODE_STRICT, device: int = 0, rank: int = 0, nranks: int = 1,
-                nx_local: int | None = None, variant: int = 0) -> capi.Solver:
+                nx_local: int | None = None, variant: int = 0, halo_steps: int = 0) -> capi.Solver:
     _, _, _, dt_on_dx, dt_on_dy = time_constants(pb)
     return capi.Solver(pb.dims, nx_local if nx_local is not None else pb.nx, pb.ny, order=pb.order, bc=pb.bc,
                        limiter=pb.limiter, tform=pb.tform, mode=mode, alpha=pb.alpha, dt_on_dx=float(dt_on_dx),
-                       dt_on_dy=float(dt_on_dy), device=device, rank=rank, nranks=nranks, variant=variant)
+                       dt_on_dy=float(dt_on_dy), device=device, rank=rank, nranks=nranks, variant=variant, halo_steps=halo_steps)
 
 
 def run_program(pb: Problem, mode: int = capi.MODE_STRICT, nsteps: int | None = None, device: int = 0, variant: int = 0):

@@ -151,3 +151,47 @@ def test_host_programs_write_the_same_results_with_slabs(manifest, tmp_path):
     pr = subprocess.run([os.path.join(HOST, "base_shll"), "64"], cwd=tmp_path, env=dict(os.environ, SHLL_NGPUS="3", SHLL_DEVICES="0,0"),
                         capture_output=True, text=True)
     assert pr.returncode != 0 and "SHLL_DEVICES" in pr.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("K", [1, 2, 5, 16])
+@pytest.mark.parametrize("order", [1, 2])
+def test_1d_temporal_halo_blocking_any_round_length_is_bitwise_the_single_slab_run(K, order, monkeypatch):
+    """1D slabs exchange K*order halo cells once every K steps (csrc/step1d.cuh, include/shll_b200.h: halo_steps).  Any K, any
+    split of the step count over shll_run calls (rounds straddle calls), a re-upload in the middle of a round, ragged slab
+    sizes, 2 / 3 / 5 slabs: the bits of one slab.  Random state, both arithmetic modes, streaming kernels (N above the tile)."""
+    import zlib
+    from shll_sve_cfd_b200 import capi, programs
+    from test_gpu_parity import _random_state
+    monkeypatch.setenv("SHLL_HALO_K", str(K))
+    monkeypatch.setenv("SHLL_PERSIST", "0")          # the single-slab comparison run uses the streaming kernels too
+    monkeypatch.setenv("SHLL_GRAPH", "0")
+    base = programs.BASE_SHLL if order == 1 else programs.SECOND_ORDER_1D
+    for n, nslabs in ((1003, 2), (4099, 3), (777, 5)):
+        pb = base.resized(n)
+        u0 = _random_state(pb, seed=zlib.crc32(f"{n}-{K}-{order}".encode()) % 1000)
+        for mode in (capi.MODE_STRICT, capi.MODE_FAST):
+            with _group(pb, mode, 1, None) as g1:
+                g1.upload_u(u0); g1.run(7); g1.run(30); mid = g1.download_u()
+                g1.upload_u(mid); g1.run(21); want = g1.download_u()
+            with _group(pb, mode, nslabs, [0] * nslabs) as g:
+                g.upload_u(u0)
+                g.run(7); g.run(30)                 # 37 steps: not a multiple of any K > 1
+                got_mid = g.download_u()
+                assert np.array_equal(bits(got_mid), bits(mid)), f"N={n} slabs={nslabs} K={K} order={order} mode={mode}: mid state"
+                g.upload_u(got_mid)                 # new state in the middle of a round: rounds restart here
+                g.run(1); g.run(20)
+                got = g.download_u()
+                stats = capi.lib().shll_halo_wait_stats
+            assert np.array_equal(bits(got), bits(want)), f"N={n} slabs={nslabs} K={K} order={order} mode={mode}"
+
+
+@pytest.mark.gpu
+def test_halo_steps_must_fit_the_slab_and_the_mailbox():
+    from shll_sve_cfd_b200 import capi
+    for kw in (dict(nx=40, order=2, halo_steps=17), dict(nx=20, order=2, halo_steps=16), dict(nx=10, order=1, halo_steps=11)):
+        with pytest.raises(capi.ShllError) as ei:
+            capi.Solver(1, kw["nx"], order=kw["order"], rank=0, nranks=2, halo_steps=kw["halo_steps"])
+        assert ei.value.code == capi.E_INVAL and "halo_steps" in str(ei.value)
+    capi.Solver(1, 64, order=2, rank=0, nranks=2, halo_steps=16).close()
+    capi.Solver(1, 64, order=2, rank=0, nranks=1, halo_steps=99).close()    # a single slab ignores it
