@@ -31,6 +31,7 @@ constexpr int HALO_ROWS = 2;
 constexpr int FLAG_WORDS = 1024;
 constexpr int MAIL_OFF = 128;
 constexpr int WAIT_STATS_OFF = 16;
+constexpr int EARLY_MAX = 1536;  // blocks of a 1D step launch that may start on their neighbours' flags (~2.5 resident waves)
 
 inline size_t mail_index(int side, unsigned round, int k) { return MAIL_OFF + (size_t)(((side * 2 + (int)(round & 1u)) * 3 + k) * HALO1D_MAX); }
 
@@ -67,6 +68,11 @@ struct shll_ctx {
     unsigned round;        // exchange rounds completed since creation (monotonic; the 1D halo flags are expressed in it)
     unsigned sends;        // send steps launched since creation
     unsigned origin;       // state_index at the last upload: rounds restart there
+    // 1D: early start of the first wave of blocks (step1d.cuh)
+    unsigned *done;        // per-block done flags, EARLY_MAX + 2 words
+    unsigned early_epoch;  // value published by the last step launch that used the early-start protocol
+    int early_prev_grid;   // ... and its grid size
+    int sms;               // multiprocessors of the device
     KernelKey key;
     int ntiles, nchunks;
     CUtensorMap tmap[2];   // 2D TMA kernels: one 3D map {ny, nx+4, 4} per ping-pong buffer
@@ -303,6 +309,8 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
         c->plane_elems = round_up((size_t)(g.nx + 2 * HALO_ROWS) * g.ny, 64);
     }
     c->halo_K = g.halo_steps;
+    c->sms = 148;
+    if (cudaDeviceGetAttribute(&c->sms, cudaDevAttrMultiProcessorCount, g.device) != cudaSuccess || c->sms < 1) { (void)cudaGetLastError(); c->sms = 148; }
     c->key.order = g.order;
     c->key.bc = g.bc;
     c->key.lim = g.limiter;
@@ -332,6 +340,10 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     CKC(cudaMalloc(&c->state, state_bytes));
     CKC(cudaMalloc(&c->flags, FLAG_WORDS * sizeof(unsigned)));
     CKC(cudaMemsetAsync(c->flags, 0, FLAG_WORDS * sizeof(unsigned), c->stream));
+    if (g.dims == 1) {
+        CKC(cudaMalloc(&c->done, (EARLY_MAX + 2) * sizeof(unsigned)));
+        CKC(cudaMemsetAsync(c->done, 0, (EARLY_MAX + 2) * sizeof(unsigned), c->stream));
+    }
     // Fill everything (halos, padding) with a benign gas state (1.0f bit pattern) so unused lanes never see NaNs.
     fill_kernel<<<1024, 256, 0, c->stream>>>(c->state, 1.0f, state_bytes / sizeof(float));
     CKC(cudaGetLastError());
@@ -341,6 +353,12 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
         if (rc != 0) {  // not fatal: the LDG kernel computes the same bits
             plan_2d(c, /*no_tma=*/true);
         }
+    }
+    if (g.dims == 2 && c->key.tma) {  // early-start flags, one per (chunk, tile) block of a step launch (step2d_tma.cuh)
+        const size_t nflags = (size_t)c->ntiles * c->nchunks;
+        CKC(cudaMalloc(&c->done, nflags * sizeof(unsigned)));
+        CKC(cudaMemsetAsync(c->done, 0, nflags * sizeof(unsigned), c->stream));
+        CKC(cudaStreamSynchronize(c->stream));
     }
     snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? (c->key.acc ? "_tma_acc" : "_tma") : ((g.dims == 1 && c->key.acc) ? "_acc" : ""),
              g.order, g.bc == SHLL_BC_REFLECT ? "reflect" : "outflow", g.order == 2 ? (g.limiter == SHLL_LIM_MC ? "mc_" : "minmod_") : "",
@@ -365,6 +383,7 @@ int shll_destroy(shll_ctx *c)
     if (c->tmap_dev) cudaFree(c->tmap_dev);
     if (c->sums_dev) cudaFree(c->sums_dev);
     if (c->graph) cudaGraphExecDestroy(c->graph);
+    if (c->done) cudaFree(c->done);
     if (c->strips) cudaFree(c->strips);
     if (c->round_done) cudaFree(c->round_done);
     if (c->state) cudaFree(c->state);
@@ -470,7 +489,7 @@ int launch_one_step(shll_ctx *c)
         S.timeout_ns = (unsigned long long)env_int("SHLL_HALO_TIMEOUT_MS", 5000) * 1000000ull;
         S.wait_ns = reinterpret_cast<unsigned long long *>(c->flags + WAIT_STATS_OFF);
     }
-    bool sent = false;
+    bool sent = false, early2d = false;
     cudaError_t e;
     if (g.dims == 2) {
         Step2DParams P;
@@ -501,7 +520,24 @@ int launch_one_step(shll_ctx *c)
             T.stages = c->tma_stages;
             // consecutive steps of a single-GPU run overlap their launch with the predecessor's tail (step2d_acc.cu)
             T.pdl = use_pdl(c);
+            T.early_blocks = 0; T.early_want = 0; T.early_post = 0; T.done = nullptr; T.early_err = c->flags + 4;
+            // Measured (profiles/r02_early_start.log), with the publishers restricted to the blocks an early block can depend on
+            // (with every block publishing, the release fences cost the 14 us blocks of the 1st-order FAST kernel more than the
+            // overlapped ramp-up saved: 89.3 -> 97.6 us): FAST 2nd order 112.8 -> 117.0 Gcu/s, FAST 1st order 188.1 -> 190.6,
+            // STRICT 80.0 -> 86.8 / 42.4 -> 45.0.  Only on grids of at least 4 resident waves; launch-bound small grids keep the
+            // plain wait.  SHLL_EARLY=2 forces it on, 0 off.
+            const int early_mode = env_int("SHLL_EARLY", 1);
+            const int wave = c->sms * (g.order == 1 ? 16 : 12);             // resident one-warp blocks
+            const bool long_blocks = warps >= 4 * wave;
+            if (T.pdl && c->done && (early_mode == 2 || (early_mode == 1 && long_blocks))) {
+                T.early_blocks = env_int("SHLL_EARLY_BLOCKS", wave * 3 / 2);
+                if (T.early_blocks > warps) T.early_blocks = warps;
+                T.early_want = c->early_epoch;
+                T.early_post = c->early_epoch + 1;
+                T.done = c->done;
+            }
             dim3 grid(warps);
+            early2d = (T.done != nullptr);
             if (c->key.acc) e = launch_step2d_acc(c->key, T, grid, c->tma_smem, c->stream);
             else if (g.order == 1) e = launch_step2d_tma_o1(c->key, T, grid, c->tma_smem, c->stream);
             else if (g.mode == SHLL_MODE_STRICT) e = launch_step2d_tma_o2_strict(c->key, T, grid, c->tma_smem, c->stream);
@@ -547,7 +583,8 @@ int launch_one_step(shll_ctx *c)
         // 4 (face-flux kernel: 8) consecutive tiles per warp on large tubes (B200 sweep: profiles/); small tubes keep one warp
         // per tile so that all SMs work
         const int tpw_big = c->key.acc ? 8 : 4;
-        P.tiles_per_warp = env_int("SHLL_1D_TILES_PER_WARP", P.ntiles >= tpw_big * 4096 ? tpw_big : (P.ntiles >= 4096 ? P.ntiles / 4096 : 1));
+        const int ntiles_real = (g.nx + 119) / 120;  // (from the slab itself, not from this step's extended range: the same every step)
+        P.tiles_per_warp = env_int("SHLL_1D_TILES_PER_WARP", ntiles_real >= tpw_big * 4096 ? tpw_big : (ntiles_real >= 4096 ? ntiles_real / 4096 : 1));
         if (P.tiles_per_warp < 1) P.tiles_per_warp = 1;
         if (m) {  // the 1D flags count exchange ROUNDS, the arrival counters count send steps
             S.want = c->round + 1;
@@ -560,10 +597,24 @@ int launch_one_step(shll_ctx *c)
         P.pdl = use_pdl(c);
         const int warps = (P.ntiles + P.tiles_per_warp - 1) / P.tiles_per_warp;  // a warp marches through consecutive tiles
         dim3 block(128), grid((warps + 3) / 4);
+        // first wave starts on its neighbours' flags (only meaningful in a chain of programmatic launches; >= 4 blocks of 480*tpw cells
+        // so that a block's cells stay within its own and its neighbours' blocks from one launch to the next)
+        // (decided from the slab itself so that it is the same for every launch of the context)
+        const int grid_real = ((ntiles_real + P.tiles_per_warp - 1) / P.tiles_per_warp + 3) / 4;
+        if (P.pdl && c->done && grid_real >= 6 && env_int("SHLL_EARLY", 1) != 0) {
+            P.early_blocks = (int)grid.x - 1 < EARLY_MAX ? (int)grid.x - 1 : EARLY_MAX;
+            P.early_want = c->early_epoch;
+            P.early_post = c->early_epoch + 1;
+            P.early_prev_grid = c->early_prev_grid;
+            P.done = c->done;
+            P.early_err = c->flags + 4;
+        }
         e = launch_step1d(c->key, P, grid, block, c->stream);
+        if (e == cudaSuccess && P.early_blocks > 0) { c->early_epoch++; c->early_prev_grid = (int)grid.x; }
         sent = send;
     }
     if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "step kernel launch failed (%s): %s", c->variant, cudaGetErrorString(e));
+    if (early2d) c->early_epoch++;
     c->cur = outb;
     c->state_index++;
     c->epoch++;
@@ -636,10 +687,11 @@ int run_persistent_1d(shll_ctx *c, long nsteps)
 
 int check_halo_error(shll_ctx *c)
 {
-    if (!multi(c) && !c->persist_blocks) return SHLL_OK;
+    if (!multi(c) && !c->persist_blocks && !c->early_epoch) return SHLL_OK;
     unsigned err = 0;
     CK(c, cudaMemcpyAsync(&err, c->flags + 4, sizeof(unsigned), cudaMemcpyDeviceToHost, c->stream));
     CK(c, cudaStreamSynchronize(c->stream));
+    if (err == 2u) return fail(c, SHLL_E_TIMEOUT, "a block waited more than 2 s for its neighbours of the previous step launch (early-start protocol, step1d.cuh)");
     if (err) return fail(c, SHLL_E_TIMEOUT, "rank %d: a neighbour's halo (or a neighbouring block's strip) did not arrive within the timeout", c->cfg.rank);
     return SHLL_OK;
 }

@@ -32,6 +32,13 @@ struct Step1DParams {
     int tiles_per_warp;  // step1d_acc.cuh: consecutive tiles one warp marches through (register prefetch of the next one)
     float quarter;  // 0.25f as a parameter (register operand of the one-LOP3 sign transfer, step1d_acc.cuh)
     int pdl;        // launched with programmatic stream serialization (halo_sync.cuh: pdl_wait_for_previous_step)
+    // ---- early start of the first wave (see step1d_ring_march) -----------------------------------------------------------
+    int early_blocks;        // blocks [0, early_blocks) start on their neighbours' flags instead of griddepcontrol.wait (0 = off)
+    unsigned early_want;     // value the previous step launch published in done[]
+    unsigned early_post;     // value this launch publishes
+    int early_prev_grid;     // grid size of the launch that published early_want (its blocks [0, early_prev_grid) exist)
+    unsigned *done;          // [early_blocks + 2] per-block "my output of step launch #v is visible" flags (monotonic)
+    unsigned *early_err;     // error word (shared with the halo protocol)
     // ---- multi-GPU slabs: temporal blocking of the halo exchange -------------------------------------------------------
     // Neighbouring GPUs exchange H = K*ORDER cells once every K steps instead of ORDER cells every step: a round starts with
     // the H halo cells of both sides valid, every step of the round the kernel ALSO updates the halo cells that are still
@@ -91,7 +98,30 @@ __device__ __forceinline__ void step1d_prefetch(const Step1DParams &P, int tile,
         asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(slot + k * 512u), "l"(P.in[k] + jl) : "memory");
 }
 
+__device__ __forceinline__ unsigned ld_acquire_gpu_u32(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu_u32(unsigned *p, unsigned v)
+{
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+
 // tile_fn(tile, lane, interior, cur[3]); blocks are 128 threads (4 warps); ORDER decides which tiles are interior.
+//
+// Between two step launches.  With programmatic dependent launch the blocks of step s+1 are placed while step s drains, but
+// griddepcontrol.wait holds ALL of them until the LAST block of step s has finished and flushed: every step pays the drain
+// of its predecessor plus one DRAM latency of ramp-up (4.5 us of a 36 us step at 2^23 cells, profiles/r02_1d_tiles_per_warp.log).
+// A block only needs the output of three blocks of the previous step -- the one with its own index and its two neighbours
+// (a block's cells never move by more than 36 cells from one launch to the next, step1d.cuh: ext_lo).  So the blocks of the
+// first wave [0, early_blocks) skip griddepcontrol.wait and start as soon as those three blocks have published
+// done[b] = launch id (st.release.gpu after a block barrier; ld.acquire.gpu on the consumer side): the ramp-up of step s+1
+// overlaps the drain of step s.  Later blocks are placed when step s is long over and keep the plain wait.  Write-after-read
+// is covered by the same flags: the block that overwrites cells of buffer X has seen its neighbours -- the only readers of
+// those cells in the previous launch -- finish.  No deadlock: a launch only starts once every block of its predecessor has
+// STARTED (they all call griddepcontrol.launch_dependents first), so the blocks it waits for are resident or done.
 template <class F>
 __device__ __forceinline__ void step1d_ring_march(const Step1DParams &P, F &&tile_fn, int order)
 {
@@ -99,36 +129,62 @@ __device__ __forceinline__ void step1d_ring_march(const Step1DParams &P, F &&til
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
     const int w = blockIdx.x * (blockDim.x >> 5) + wib;
     const int t0 = w * P.tiles_per_warp, t1 = min(t0 + P.tiles_per_warp, P.ntiles);
-    pdl_wait_for_previous_step(P.pdl);
-    if (t0 >= t1) return;
-    const uint32_t base = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][0][lane]);
-    constexpr uint32_t STAGE_BYTES = 3 * 512;
-#pragma unroll
-    for (int s = 0; s < STEP1D_STAGES - 1; s++) {
-        if (t0 + s < t1) step1d_prefetch(P, t0 + s, lane, base + s * STAGE_BYTES);
-        asm volatile("cp.async.commit_group;" ::: "memory");
+    const int b = blockIdx.x;
+    const bool early = b < P.early_blocks;                 // block-uniform
+    if (P.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (early) {
+        if (threadIdx.x < 3) {
+            const int nb = b - 1 + (int)threadIdx.x;       // b-1, b, b+1: every one of them publishes (nb <= early_blocks)
+            if (nb >= 0 && nb < P.early_prev_grid && (int)(ld_acquire_gpu_u32(P.done + nb) - P.early_want) < 0) {
+                const unsigned long long tstart = globaltimer_ns();
+                unsigned polls = 0;
+                while ((int)(ld_acquire_gpu_u32(P.done + nb) - P.early_want) < 0) {
+                    __nanosleep(20);
+                    if ((++polls & 1023u) == 0 && globaltimer_ns() - tstart > 2000000000ull) {  // never hang the GPU
+                        atomicExch(P.early_err, 2u);
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    } else if (P.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
     }
-    int stage = 0;
-    for (int tile = t0; tile < t1; tile++) {
-        {   // refill the stage whose tile was consumed in the previous iteration
-            const int ahead = tile + STEP1D_STAGES - 1;
-            int fill = stage + STEP1D_STAGES - 1;
-            if (fill >= STEP1D_STAGES) fill -= STEP1D_STAGES;
-            if (ahead < t1) step1d_prefetch(P, ahead, lane, base + fill * STAGE_BYTES);
+    if (t0 < t1) {
+        const uint32_t base = (uint32_t)__cvta_generic_to_shared(&ring[wib][0][0][lane]);
+        constexpr uint32_t STAGE_BYTES = 3 * 512;
+#pragma unroll
+        for (int s = 0; s < STEP1D_STAGES - 1; s++) {
+            if (t0 + s < t1) step1d_prefetch(P, t0 + s, lane, base + s * STAGE_BYTES);
             asm volatile("cp.async.commit_group;" ::: "memory");
         }
-        asm volatile("cp.async.wait_group %0;" ::"n"(STEP1D_STAGES - 1) : "memory");
-        float4 cur[3];
+        int stage = 0;
+        for (int tile = t0; tile < t1; tile++) {
+            {   // refill the stage whose tile was consumed in the previous iteration
+                const int ahead = tile + STEP1D_STAGES - 1;
+                int fill = stage + STEP1D_STAGES - 1;
+                if (fill >= STEP1D_STAGES) fill -= STEP1D_STAGES;
+                if (ahead < t1) step1d_prefetch(P, ahead, lane, base + fill * STAGE_BYTES);
+                asm volatile("cp.async.commit_group;" ::: "memory");
+            }
+            asm volatile("cp.async.wait_group %0;" ::"n"(STEP1D_STAGES - 1) : "memory");
+            float4 cur[3];
 #pragma unroll
-        for (int k = 0; k < 3; k++)
-            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                         : "=f"(cur[k].x), "=f"(cur[k].y), "=f"(cur[k].z), "=f"(cur[k].w)
-                         : "r"(base + stage * STAGE_BYTES + k * 512u)
-                         : "memory");
-        // interior tile: all 128 loaded cells and their +-ORDER neighbours are real owned cells of this slab
-        const bool interior = (tile > 0) && ((long)tile * 120 + 124 + order <= (long)P.interior_end - order);
-        tile_fn(tile, lane, interior, cur);
-        if (++stage == STEP1D_STAGES) stage = 0;
+            for (int k = 0; k < 3; k++)
+                asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                             : "=f"(cur[k].x), "=f"(cur[k].y), "=f"(cur[k].z), "=f"(cur[k].w)
+                             : "r"(base + stage * STAGE_BYTES + k * 512u)
+                             : "memory");
+            // interior tile: all 128 loaded cells and their +-ORDER neighbours are real owned cells of this slab
+            const bool interior = (tile > 0) && ((long)tile * 120 + 124 + order <= (long)P.interior_end - order);
+            tile_fn(tile, lane, interior, cur);
+            if (++stage == STEP1D_STAGES) stage = 0;
+        }
+    }
+    if (b <= P.early_blocks && P.early_blocks > 0) {       // publishers: the first wave and the block after it
+        __syncthreads();                                   // every warp of the block has issued its stores
+        if (threadIdx.x == 0) st_release_gpu_u32(P.done + b, P.early_post);
     }
 }
 

@@ -484,7 +484,7 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    pdl_wait_for_previous_step(T.pdl);  // everything above only touched registers and shared memory
+    step2d_wait_for_input(T, tile, chunk, lane);  // everything above only touched registers and shared memory
     if (lane == 0) {
         for (int b = 0; b < X.stages && b < X.nboxes; b++) X.arm(b, b);
     }
@@ -494,6 +494,7 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
     else if (T.tma_store) acc_march<ORDER, BC, LIM, false, STASH, true>(X, W, rbeg, rlast, lane, tile);
     else acc_march<ORDER, BC, LIM, false, STASH, false>(X, W, rbeg, rlast, lane, tile);
 
+    step2d_publish_output(T, tile, chunk, lane);
     if (P.sync.enabled) {
         if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);
         if (touch_hi) halo_arrive(P.sync, P.sync.cnt_hi, P.sync.edge_warps_hi, P.sync.sig_hi);

@@ -30,6 +30,14 @@ struct Step2DTmaParams {
     CUtensorMap tmap;     // INPUT buffer as a 3D tensor {ny, nx+4, 4 planes}, origin = halo row -2 of plane 0
     CUtensorMap tmap_out; // step2d_acc.cuh: OUTPUT buffer, same tensor, box = 60 owned columns x 4 rows x 4 planes (TMA store)
     int tma_store;        // step2d_acc.cuh: interior boxes leave through one cp.async.bulk.tensor store per box
+    // early start of the first wave (same idea as step1d.cuh: step1d_ring_march): every block publishes done[chunk*ntiles + tile]
+    // = launch id when its rows are visible; the first early_blocks blocks of the NEXT launch start on the flags of the five
+    // blocks they depend on (own, tile +-1, chunk +-1 -- the stencil is a cross, box corners are loaded but never used)
+    // instead of griddepcontrol.wait, so the ramp-up of a step overlaps the drain of its predecessor.
+    int early_blocks;
+    unsigned early_want, early_post;
+    unsigned *done;       // [nchunks * ntiles]
+    unsigned *early_err;
     const CUtensorMap *tmap_global;  // optional copy of the same descriptor in device memory (debug switch SHLL_TMAP_GLOBAL)
     int stages;
     int pdl;              // launched with programmatic stream serialization: the kernel waits for its predecessor itself (halo_sync.cuh)
@@ -65,6 +73,61 @@ __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
         "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
         : "memory");
+}
+
+__device__ __forceinline__ unsigned ld_acquire_gpu2d(const unsigned *p)
+{
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// Start of a 2D step block (one warp): let the successor launch be placed, then wait for the input -- the whole previous
+// launch (griddepcontrol.wait), or, for the first wave, just the five blocks of it this block reads from / overwrites after.
+__device__ __forceinline__ void step2d_wait_for_input(const Step2DTmaParams &T, int tile, int chunk, int lane)
+{
+    if (T.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    // (launch order: chunk 0, the LAST chunk, 1, 2, ... -- the last chunk's lower neighbour finishes at the very end of a launch,
+    // so its blocks keep the plain wait)
+    const bool last_chunk_slot = T.base.nchunks > 2 && (int)blockIdx.x >= T.base.ntiles && (int)blockIdx.x < 2 * T.base.ntiles;
+    if ((int)blockIdx.x < T.early_blocks && !last_chunk_slot) {
+        const Step2DParams &P = T.base;
+        if (lane < 5) {
+            // lane 0: own block; 1, 2: tile -+ 1; 3, 4: chunk -+ 1
+            const int dt = (lane == 1) ? -1 : (lane == 2 ? 1 : 0), dc = (lane == 3) ? -1 : (lane == 4 ? 1 : 0);
+            const int t = tile + dt, c = chunk + dc;
+            if (t >= 0 && t < P.ntiles && c >= 0 && c < P.nchunks) {
+                const unsigned *f = T.done + (size_t)c * P.ntiles + t;
+                if ((int)(ld_acquire_gpu2d(f) - T.early_want) < 0) {
+                    const unsigned long long tstart = globaltimer_ns();
+                    unsigned polls = 0;
+                    while ((int)(ld_acquire_gpu2d(f) - T.early_want) < 0) {
+                        __nanosleep(20);
+                        if ((++polls & 1023u) == 0 && globaltimer_ns() - tstart > 2000000000ull) {  // never hang the GPU
+                            atomicExch(T.early_err, 2u);
+                            break;
+                        }
+                    }
+                }
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");  // the rows are read through the async proxy (TMA)
+        }
+        __syncwarp();
+    } else if (T.pdl) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+}
+// End of a 2D step block: every lane's stores (and lane 0's TMA stores, already waited for) are issued.
+__device__ __forceinline__ void step2d_publish_output(const Step2DTmaParams &T, int tile, int chunk, int lane)
+{
+    // publishers: every block an early block of the next launch may depend on (its own launch slot, tile +-1, chunk +-1)
+    if (T.done != nullptr && (int)blockIdx.x < T.early_blocks + T.base.ntiles + 1) {
+        __syncwarp();
+        if (lane == 0) {
+            asm volatile("fence.proxy.async;" ::: "memory");
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(T.done + (size_t)chunk * T.base.ntiles + tile), "r"(T.early_post) : "memory");
+        }
+    }
 }
 
 // TMA store: shared -> global, tracked by the issuing thread's bulk async-groups.
@@ -212,7 +275,7 @@ __global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ 
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    pdl_wait_for_previous_step(T.pdl);
+    step2d_wait_for_input(T, tile, chunk, lane);
     if (lane == 0) {
         for (int b = 0; b < X.stages && b < X.nboxes; b++) X.arm(b, b);
     }
@@ -296,6 +359,7 @@ __global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ 
             next_box();
         }
     }
+    step2d_publish_output(T, tile, chunk, lane);
     if (P.sync.enabled) {  // publish: our edge rows of this step have landed in the neighbours' halo rows
         if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);
         if (touch_hi) halo_arrive(P.sync, P.sync.cnt_hi, P.sync.edge_warps_hi, P.sync.sig_hi);

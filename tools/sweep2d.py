@@ -17,6 +17,9 @@ def main():
     steps = int(os.environ.get("SWEEP_STEPS", "200"))
     if which == "o1":
         pb = programs.BASE_SHLL_2D.resized(4096, 4096)
+    elif which.startswith("o1:") or which.startswith("o2:"):      # e.g. o1:1024 -> the reference's own sizes
+        n = int(which.split(":")[1])
+        pb = (programs.BASE_SHLL_2D if which[1] == "1" else programs.SECOND_ORDER_2D).resized(n, n)
     else:
         pb = replace(programs.SECOND_ORDER_2D.resized(2048, 16384), lx=2048 / 16384, ly=1.0)
     u0 = programs.cons_from_prim(pb, programs.initial_primitives(pb))
@@ -28,7 +31,7 @@ def main():
             else:
                 os.environ[k] = v
         try:
-            with programs.make_solver(pb, capi.MODE_FAST) as s:
+            with programs.make_solver(pb, capi.MODE_STRICT if os.environ.get("SWEEP_MODE") == "strict" else capi.MODE_FAST) as s:
                 s.upload_u(u0)
                 s.run(30)
                 s.sync()
