@@ -184,11 +184,16 @@ __device__ __forceinline__ void acc_row_y(const YEdge<2> &Y, const Step2DParams 
             const float up = __shfl_up_sync(full, hp[k].y, 1), dn = __shfl_down_sync(full, hg[k].x, 1);
             ysum = v2sub(v2add(hp[k], hg[k]), v2mk(fadd(hg[k].y, up), fadd(dn, hp[k].x)));
         } else {
-            // backward differences d[j] = H[j] - H[j-1]; the forward difference of cell j is d[j+1]
-            const v2 dlp = v2mk(fsub(hp[k].x, __shfl_up_sync(full, hp[k].y, 1)), fsub(hp[k].y, hp[k].x));
-            const v2 dlm = v2mk(fsub(hg[k].x, __shfl_up_sync(full, hg[k].y, 1)), fsub(hg[k].y, hg[k].x));
-            const v2 drp = v2mk(dlp.y, __shfl_down_sync(full, dlp.x, 1));
-            const v2 drm = v2mk(dlm.y, __shfl_down_sync(full, dlm.x, 1));
+            // backward differences d[j] = H[j] - H[j-1]; the forward difference of cell j is d[j+1].  The forward difference of
+            // the lane's upper cell is computed here from the neighbour lane's H (the very subtraction that lane performs for its
+            // own backward difference: same operands, same bits) rather than fetched from it -- all four shuffles of a component
+            // then depend on the fluxes only, one level of shuffle latency less on the critical path of the row.
+            const float hp_up = __shfl_up_sync(full, hp[k].y, 1), hp_dn = __shfl_down_sync(full, hp[k].x, 1);
+            const float hg_up = __shfl_up_sync(full, hg[k].y, 1), hg_dn = __shfl_down_sync(full, hg[k].x, 1);
+            const v2 dlp = v2mk(fsub(hp[k].x, hp_up), fsub(hp[k].y, hp[k].x));
+            const v2 dlm = v2mk(fsub(hg[k].x, hg_up), fsub(hg[k].y, hg[k].x));
+            const v2 drp = v2mk(dlp.y, fsub(hp_dn, hp[k].y));
+            const v2 drm = v2mk(dlm.y, fsub(hg_dn, hg[k].y));
             const v2 psi = v2fma(limiter_weight(dlp, drp, q), limiter_magnitude<LIM>(dlp, drp, P.alpha), hp[k]);      // H+ + dH+/2
             const v2 gam = v2fma(limiter_weight_neg(dlm, drm, nq), limiter_magnitude<LIM>(dlm, drm, P.alpha), hg[k]);  // -(H- - dH-/2)
             const float up = __shfl_up_sync(full, psi.y, 1), dn = __shfl_down_sync(full, gam.x, 1);

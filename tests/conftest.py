@@ -57,7 +57,9 @@ FAST_TOL_LONG = {
     # case (tests/golden/<case>.npz, made by tests/golden/make_golden_long.py from the compiled reference): tolerance
     "long_2d_o1_1024": 3e-5,    # base_shll_2d.c, 1024^2, 820 steps to t = 0.1 (README Table 9 size)
     "long_2d_o2_256": 1e-4,     # 2nd_order_base_shll.c as checked in: 256^2, 1639 steps to t = 0.8
-    "long_omp_o2_128": 3e-5,    # base-omp/2nd_order_base_shll.c (MC limiter, configuration 6), 128^2, 308 steps to t = 0.3
+    "long_omp_o2_128": 3e-5,
+    "long_1d_o2_65536": 1e-4,   # BASELINE.json configs[1]: derived 1D 2nd order, 65 536 cells, 104 858 steps (fixture from the oracle,
+                                # tests/golden/make_golden_config1.py; no FMA-sensitivity anchor recorded for it)    # base-omp/2nd_order_base_shll.c (MC limiter, configuration 6), 128^2, 308 steps to t = 0.3
 }
 
 

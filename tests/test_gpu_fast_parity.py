@@ -166,7 +166,7 @@ def test_fast_random_state_all_scheme_combinations(scheme, oracle):
 
 # ------------------------------------------------------------------------------------ full-length FAST runs
 
-@pytest.mark.parametrize("case", sorted(FAST_TOL_LONG))
+@pytest.mark.parametrize("case", sorted(c for c in FAST_TOL_LONG if c != "long_1d_o2_65536"))   # (that one: test_gpu_parity.py)
 def test_fast_full_length_runs_within_the_stated_long_run_tolerance(case):
     """The reference programs run to their own end time (820 / 1639 / 308 steps) in FAST mode, final primitive fields as
     shll_download_p returns them against the compiled reference's dump (committed fixture, tests/golden/make_golden_long.py).

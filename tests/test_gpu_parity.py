@@ -389,3 +389,24 @@ def test_exactness_shortcuts_device_selftest():
         assert (1 << 20) < r[flagged] < r[total] - (1 << 26), (flagged, r)
     r2 = capi.selftest_exact_division(1 << 22, seed=7)
     assert sum(r2[k] for k in r2 if k.endswith("mismatch")) == 0, r2
+
+
+def test_config1_65536_cells_run_to_completion_is_bit_exact():
+    """BASELINE.json configs[1] exactly: the derived 1D 2nd-order program at 65 536 cells, all 104 858 steps to t = 0.2 in ONE
+    persistent cooperative launch, STRICT mode, bit for bit against the full-length fixture (tests/golden/make_golden_config1.py);
+    FAST mode within the long-run tolerance table (conftest.FAST_TOL_LONG)."""
+    import os
+    from conftest import FAST_TOL_LONG, GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "long_1d_o2_65536.npz"))
+    pb = programs.SECOND_ORDER_1D.resized(65536)
+    r = programs.run_program(pb, capi.MODE_STRICT)
+    assert r["steps"] == 104858 == int(z["steps"])
+    assert r["launches"] <= 2, r["launches"]          # the march itself is one launch (+ the device-side Compute_P_from_U)
+    bad = int((bits(r["u"]) != bits(z["u"])).sum())
+    assert bad == 0, f"{bad} words differ after 104858 steps, max |du| = {np.abs(r['u'] - z['u']).max()}"
+    assert np.array_equal(bits(r["p"]), bits(z["p"]))
+    f = programs.run_program(pb, capi.MODE_FAST)
+    ref = z["p"].astype(np.float64)
+    rel = float((np.abs(f["p"].astype(np.float64) - ref) / (1.0 + np.abs(ref))).max())
+    print(f"[fast long run] long_1d_o2_65536: 104858 steps, {f['variant']}: max |dp|/(1+|p|) = {rel:.3e}")
+    assert rel <= FAST_TOL_LONG["long_1d_o2_65536"], rel
