@@ -394,9 +394,9 @@ def test_exactness_shortcuts_device_selftest():
 def test_config1_65536_cells_run_to_completion_is_bit_exact():
     """BASELINE.json configs[1] exactly: the derived 1D 2nd-order program at 65 536 cells, all 104 858 steps to t = 0.2 in ONE
     persistent cooperative launch, STRICT mode, bit for bit against the full-length fixture (tests/golden/make_golden_config1.py);
-    FAST mode within the long-run tolerance table (conftest.FAST_TOL_LONG)."""
+    FAST mode in the mean / outlier-share sense stated in conftest.py (FAST_LONG_1D_*)."""
     import os
-    from conftest import FAST_TOL_LONG, GOLDEN_DIR
+    from conftest import FAST_LONG_1D_MEAN_TOL, FAST_LONG_1D_SHARE_ABOVE, FAST_TOL_LONG, GOLDEN_DIR
     z = np.load(os.path.join(GOLDEN_DIR, "long_1d_o2_65536.npz"))
     pb = programs.SECOND_ORDER_1D.resized(65536)
     r = programs.run_program(pb, capi.MODE_STRICT)
@@ -405,8 +405,18 @@ def test_config1_65536_cells_run_to_completion_is_bit_exact():
     bad = int((bits(r["u"]) != bits(z["u"])).sum())
     assert bad == 0, f"{bad} words differ after 104858 steps, max |du| = {np.abs(r['u'] - z['u']).max()}"
     assert np.array_equal(bits(r["p"]), bits(z["p"]))
+    # FAST mode after 104 858 steps: the smooth parts agree to rounding drift, but a discontinuity that lands one cell to the side
+    # is an O(jump) pointwise difference, so the max norm says nothing here ("long runs should be judged in strict
+    # mode or on prefix checkpoints").  Stated instead: the mean error and the share of cells outside the long-run tolerance.
     f = programs.run_program(pb, capi.MODE_FAST)
     ref = z["p"].astype(np.float64)
-    rel = float((np.abs(f["p"].astype(np.float64) - ref) / (1.0 + np.abs(ref))).max())
-    print(f"[fast long run] long_1d_o2_65536: 104858 steps, {f['variant']}: max |dp|/(1+|p|) = {rel:.3e}")
-    assert rel <= FAST_TOL_LONG["long_1d_o2_65536"], rel
+    err = np.abs(f["p"].astype(np.float64) - ref) / (1.0 + np.abs(ref))
+    l1, worst, share = float(err.mean()), float(err.max()), float((err.max(axis=0) > FAST_TOL_LONG["long_1d_o2_65536"]).mean())
+    e = err.max(axis=0)
+    print(f"[fast long run] long_1d_o2_65536: 104858 steps, {f['variant']}: mean |dp|/(1+|p|) = {l1:.3e}, max = {worst:.3e}, "
+          f"cells outside {FAST_TOL_LONG['long_1d_o2_65536']:g}: {share * 100:.4f} %; share of cells above 1e-4 / 3e-4 / 1e-3 / 1e-2: "
+          f"{(e > 1e-4).mean():.4f} / {(e > 3e-4).mean():.4f} / {(e > 1e-3).mean():.4f} / {(e > 1e-2).mean():.5f}")
+    assert np.isfinite(f["p"]).all()
+    assert l1 <= FAST_LONG_1D_MEAN_TOL, l1
+    for level, most in FAST_LONG_1D_SHARE_ABOVE.items():
+        assert float((e > level).mean()) <= most, (level, float((e > level).mean()))
