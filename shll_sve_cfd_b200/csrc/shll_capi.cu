@@ -165,10 +165,16 @@ void plan_2d(shll_ctx *c, bool no_tma = false)
         // have an item -- thinner chunks recompute more halo rows, which only matters once the GPU is full
         // (profiles/r01_sweep_chunk_height_small_grids.log: 256^2 order 2 37.9 -> 9.4 us per step, 1024^2 order 2 42.6 -> 20.3).
         const int box_rows = (g.order == 1 && !c->key.acc) ? 3 : 4;
-        const int lowest = c->key.acc ? (g.order == 1 ? 2 : 4) : box_rows;
+        const int lowest = c->key.acc ? (g.order == 1 ? 2 : 4) : (g.order == 1 ? 6 : 4);
         int sms = 148;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device) != cudaSuccess || sms < 1) { (void)cudaGetLastError(); sms = 148; }
-        const long want = (long)sms * (g.order == 1 ? 16 : 12) / 2;
+        // Blocks wanted before the chunks stop shrinking, in units of one resident wave of one-warp blocks (B200 sweep over the
+        // reference's own grid sizes 256^2 .. 2048^2 and the full sizes, profiles/r02_sweep_chunk_height_reference_sizes.log):
+        // FAST kernels are content with 3/4 (order 1) or 1/2 (order 2) of a wave; the STRICT kernels, whose rows take ~3x longer,
+        // balance best with ~5 (order 1: 1024^2 57.7 -> 34.7 us per step, 2048^2 96.5 -> 78.3) or ~2.25 (order 2: 1024^2 85 -> 51) waves.
+        const long wave = (long)sms * (g.order == 1 ? 16 : 12);
+        const long want = (g.mode == SHLL_MODE_FAST && c->key.acc) ? (g.order == 1 ? wave * 3 / 4 : wave / 2)
+                                                                    : (g.order == 1 ? wave * 5 : wave * 9 / 4);
         while (rpc - box_rows >= lowest && (long)c->ntiles * ((g.nx + rpc - 1) / rpc) < want) rpc -= box_rows;
     }
     if (rpc < 2) rpc = 2;

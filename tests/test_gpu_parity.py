@@ -280,7 +280,7 @@ def test_programmatic_dependent_launch_does_not_change_bits(pb, monkeypatch):
 
 
 def test_small_2d_grids_get_thinner_chunks():
-    """plan_2d shrinks the chunk height until about half the resident warp slots have an item."""
+    """plan_2d shrinks the chunk height until the launch has enough blocks for the kernel at hand."""
     def chunks(pb, mode):
         with programs.make_solver(pb, mode) as s:
             return int(s.variant.split("_chunks")[1].split("_")[0])
@@ -288,6 +288,10 @@ def test_small_2d_grids_get_thinner_chunks():
     assert chunks(programs.BASE_SHLL_2D.resized(256, 256), capi.MODE_FAST) == 128        # 2-row chunks
     assert chunks(programs.BASE_SHLL_2D.resized(4096, 4096), capi.MODE_FAST) == 228      # the tuned 18 rows at configs[2]
     assert chunks(programs.SECOND_ORDER_2D.resized(2048, 16384), capi.MODE_FAST) == 32   # the tuned 64 rows at configs[4]
+    assert chunks(programs.BASE_SHLL_2D.resized(1024, 1024), capi.MODE_FAST) == 103      # 10-row chunks: 3/4 of a resident wave
+    assert chunks(programs.BASE_SHLL_2D.resized(1024, 1024), capi.MODE_STRICT) == 171    # 6-row chunks: the bit-exact rows are ~3x longer
+    assert chunks(programs.BASE_SHLL_2D.resized(4096, 4096), capi.MODE_STRICT) == 171    # the tuned 24 rows at full size
+    assert chunks(programs.SECOND_ORDER_2D.resized(1024, 1024), capi.MODE_STRICT) == 128  # 8-row chunks
 
 
 def test_cfl_diagnostic_and_api_state_errors(oracle):
