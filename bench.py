@@ -644,7 +644,8 @@ def main():
             "other_mode": other,
             "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s", "frac": r["achieved"] / r["peak"],
                          "traffic": tr, "traffic_source": tr_src, "peak_source": r["peak_src"],
-                         "algorithmic_bytes_per_launch": r["bytes_per_launch"], "kernel": r["variant"]},
+                         "algorithmic_bytes_per_launch": r["bytes_per_launch"] * (K // max(1, r["launches"])),
+                         "steps_per_launch": K // max(1, r["launches"]), "kernel": r["variant"]},
             "clocks": r["clocks"],
             "parity_vs_1gpu": r.get("parity_vs_1gpu"),
             "halo_exchange": r.get("halo"),

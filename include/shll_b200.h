@@ -84,10 +84,11 @@ typedef struct shll_config {
     int32_t rank;          /* slab index along x, 0 .. nranks-1 */
     int32_t nranks;        /* number of slabs; slab 0 owns the x=0 wall, slab nranks-1 the x=NX-1 wall */
     int32_t variant;       /* kernel variant: 0 = auto; otherwise a tuning id */
-    int32_t halo_steps;    /* 1D slabs (nranks > 1): time steps per halo exchange round, K.  Neighbouring GPUs exchange
-                              K*order cells once every K steps instead of `order` cells every step (temporal blocking; same
-                              bits).  Must be the same on every slab, K*order <= 32 and <= the smallest slab.  0 = 1 (exchange
-                              every step); shll_group_create and the Python slab front end choose it from the whole domain */
+    int32_t halo_steps;    /* slabs (nranks > 1): time steps per halo exchange round, K; must be the same on every slab.
+                              1D: neighbouring GPUs exchange K*order cells once every K steps instead of `order` cells every
+                              step (temporal blocking; same bits); K*order <= 32 and <= the smallest slab.
+                              2D: 1 or 2; 2 = the 1st-order FAST kernel advances two steps per launch and exchanges two rows.
+                              0 = 1 (exchange every step).  shll_plan_halo_steps() gives the value the front ends use */
     int32_t reserved[6];
 } shll_config;
 
@@ -102,6 +103,10 @@ SHLL_API const char *shll_last_error(const shll_ctx *ctx);
 /* Replays the reference's float clock `while (time < total_time) time += dt` (base_shll.c:200,208,216)
  * and returns the iteration count in *nsteps; SHLL_E_INVAL if the float clock stalls (never terminates). */
 SHLL_API int shll_count_steps(float dt, float total_time, long *nsteps);
+
+/* halo_steps for a domain described by `whole` (nx = ALL rows / cells along x) cut into `nslabs` balanced slabs: the value
+ * every slab's shll_config.halo_steps should carry (shll_group_create and shll_sve_cfd_b200/slabs.py call it). */
+SHLL_API int shll_plan_halo_steps(const shll_config *whole, int nslabs);
 
 /* Replaces Allocate (device side only).  Device buffers: ping-pong U, SoA, FP32. */
 SHLL_API int shll_create(shll_ctx **out, const shll_config *cfg);

@@ -19,7 +19,7 @@ IPC_BYTES = 64
 
 # every symbol include/shll_b200.h declares (tests check that the library exports exactly these)
 API_SYMBOLS = [
-    "shll_abi_version", "shll_last_error", "shll_count_steps", "shll_create", "shll_destroy", "shll_upload_u",
+    "shll_abi_version", "shll_last_error", "shll_count_steps", "shll_plan_halo_steps", "shll_create", "shll_destroy", "shll_upload_u",
     "shll_download_u", "shll_download_p", "shll_run", "shll_sync", "shll_run_timed", "shll_max_cfl",
     "shll_conserved_sums", "shll_selftest_exact_division",
     "shll_halo_wait_stats", "shll_launch_count", "shll_variant_name", "shll_peer_export", "shll_peer_connect",
@@ -71,6 +71,7 @@ def lib():
         L.shll_last_error.restype = C.c_char_p
         L.shll_last_error.argtypes = [C.c_void_p]
         L.shll_count_steps.argtypes = [C.c_float, C.c_float, C.POINTER(C.c_long)]
+        L.shll_plan_halo_steps.argtypes = [C.POINTER(Config), C.c_int]
         L.shll_create.argtypes = [C.POINTER(C.c_void_p), C.POINTER(Config)]
         L.shll_destroy.argtypes = [C.c_void_p]
         L.shll_upload_u.argtypes = [C.c_void_p, VPP]
@@ -115,6 +116,16 @@ def count_steps(dt, total_time) -> int:
     if rc:
         raise ShllError(rc, lib().shll_last_error(None).decode())
     return n.value
+
+
+def plan_halo_steps(dims, nx_global, ny, order, mode, nslabs, bc=BC_REFLECT, limiter=LIM_MINMOD) -> int:
+    """shll_plan_halo_steps: the halo_steps value every slab of a domain cut into `nslabs` must carry."""
+    cfg = Config()
+    cfg.struct_size = C.sizeof(Config)
+    cfg.dims, cfg.nx, cfg.ny, cfg.order, cfg.mode, cfg.bc, cfg.limiter = dims, nx_global, (ny if dims == 2 else 1), order, mode, bc, limiter
+    cfg.dt_on_dx = cfg.dt_on_dy = 0.125
+    cfg.nranks = 1
+    return int(lib().shll_plan_halo_steps(C.byref(cfg), int(nslabs)))
 
 
 def selftest_exact_division(npairs: int, seed: int = 1, device: int = 0) -> dict:

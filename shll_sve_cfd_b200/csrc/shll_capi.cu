@@ -73,6 +73,7 @@ struct shll_ctx {
     unsigned early_epoch;  // value published by the last step launch that used the early-start protocol
     int early_prev_grid;   // ... and its grid size
     int sms;               // multiprocessors of the device
+    bool fuse2;            // 2D FAST 1st order: two steps per launch (step2d_acc2_kernel) whenever at least two steps remain
     KernelKey key;
     int ntiles, nchunks;
     CUtensorMap tmap[2];   // 2D TMA kernels: one 3D map {ny, nx+4, 4} per ping-pong buffer
@@ -155,25 +156,32 @@ void plan_2d(shll_ctx *c, bool no_tma = false)
     c->key.acc = c->key.tma && vec == 2 && g.mode == SHLL_MODE_FAST && env_int("SHLL_ACC", 1) != 0;
     c->key.acc_cfg = env_int("SHLL_ACC_CFG", 1);
     if (c->key.acc_cfg < 0 || c->key.acc_cfg > 7) c->key.acc_cfg = 1;
+    // two steps per launch (step2d_acc.cuh: step2d_acc2_kernel): single slab -> decided here; slabs -> only when the front end asked
+    // for it on EVERY slab (halo_steps = 2), because neighbouring slabs must issue the same sequence of launches
+    c->fuse2 = c->key.acc && g.order == 1 && g.nx >= 8 && env_int("SHLL_FUSE2", 1) != 0 && (g.nranks == 1 || g.halo_steps == 2);
     const int hl = (g.order + vec - 1) / vec;
     const int useful = (32 - 2 * hl) * vec;
     c->ntiles = (g.ny + useful - 1) / useful;
-    int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? (g.order == 1 ? (c->key.acc ? 18 : 24) : 64) : 64);  // B200 sweeps (profiles/)
+    // B200 sweeps (profiles/).  1st-order FAST: 18 rows = 4 whole boxes + the two halo rows of a one-step launch; with two-step
+    // launches (4 halo rows per chunk) the curve is flat from 28 rows up, 44 rows = 11 whole boxes is its best point (229.9 Gcu/s at
+    // 4096^2, profiles/r02_fused_two_step.log)
+    int rpc = env_int("SHLL_ROWS_PER_CHUNK", c->key.tma ? (g.order == 1 ? (c->key.acc ? (c->fuse2 ? 44 : 18) : 24) : 64) : 64);
     if (c->key.tma && env_int("SHLL_ROWS_PER_CHUNK", 0) <= 0) {
         // Small and medium grids: the tuned chunk height leaves most of the GPU without a warp (256^2, 2nd order: 20 one-warp
         // blocks for 148 SMs).  Shrink the chunks, a TMA box of rows at a time, until about half of the resident warp slots
         // have an item -- thinner chunks recompute more halo rows, which only matters once the GPU is full
         // (profiles/r01_sweep_chunk_height_small_grids.log: 256^2 order 2 37.9 -> 9.4 us per step, 1024^2 order 2 42.6 -> 20.3).
         const int box_rows = (g.order == 1 && !c->key.acc) ? 3 : 4;
-        const int lowest = c->key.acc ? (g.order == 1 ? 2 : 4) : (g.order == 1 ? 6 : 4);
+        const int lowest = c->key.acc ? ((g.order == 1 && !c->fuse2) ? 2 : 4) : (g.order == 1 ? 6 : 4);
         int sms = 148;
         if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, g.device) != cudaSuccess || sms < 1) { (void)cudaGetLastError(); sms = 148; }
         // Blocks wanted before the chunks stop shrinking, in units of one resident wave of one-warp blocks (B200 sweep over the
         // reference's own grid sizes 256^2 .. 2048^2 and the full sizes, profiles/r02_sweep_chunk_height_reference_sizes.log):
         // FAST kernels are content with 3/4 (order 1) or 1/2 (order 2) of a wave; the STRICT kernels, whose rows take ~3x longer,
         // balance best with ~5 (order 1: 1024^2 57.7 -> 34.7 us per step, 2048^2 96.5 -> 78.3) or ~2.25 (order 2: 1024^2 85 -> 51) waves.
-        const long wave = (long)sms * (g.order == 1 ? 16 : 12);
-        const long want = (g.mode == SHLL_MODE_FAST && c->key.acc) ? (g.order == 1 ? wave * 3 / 4 : wave / 2)
+        // The two-step 1st-order kernel (12 warps per SM) is best with ~0.6 of its wave (1024^2: 16-row chunks 124.5 Gcu/s, 8 rows 102).
+        const long wave = (long)sms * ((g.order == 1 && !c->fuse2) ? 16 : 12);
+        const long want = (g.mode == SHLL_MODE_FAST && c->key.acc) ? (g.order == 1 ? (c->fuse2 ? wave * 3 / 5 : wave * 3 / 4) : wave / 2)
                                                                     : (g.order == 1 ? wave * 5 : wave * 9 / 4);
         while (rpc - box_rows >= lowest && (long)c->ntiles * ((g.nx + rpc - 1) / rpc) < want) rpc -= box_rows;
     }
@@ -266,6 +274,31 @@ int shll_count_steps(float dt, float total_time, long *nsteps)
     return SHLL_OK;
 }
 
+int shll_plan_halo_steps(const shll_config *whole, int nslabs)
+{
+    if (!whole || nslabs <= 1 || whole->struct_size != sizeof(shll_config)) return 1;
+    const int order = whole->order == 2 ? 2 : 1;
+    const int smallest = whole->nx / nslabs;  // balanced partition: slab sizes are floor or ceil of nx / nslabs
+    if (whole->dims == 1) {
+        int k = whole->halo_steps > 0 ? whole->halo_steps : env_int("SHLL_HALO_K", 16);
+        if (k > HALO1D_MAX / order) k = HALO1D_MAX / order;
+        if (k > smallest / order) k = smallest / order;
+        return k < 1 ? 1 : k;
+    }
+    // 2D: two-step launches where the 1st-order FAST face-flux kernel would be selected for a slab of the smallest size
+    if (whole->halo_steps == 1 || smallest < 16) return 1;
+    shll_ctx probe;
+    memset(&probe, 0, sizeof(probe));
+    probe.cfg = *whole;
+    probe.cfg.nx = smallest;
+    probe.cfg.nranks = nslabs;
+    probe.cfg.halo_steps = 2;
+    if (probe.cfg.tform == SHLL_TFORM_AUTO) probe.cfg.tform = SHLL_TFORM_2D;
+    probe.key.order = probe.cfg.order; probe.key.mode = probe.cfg.mode;
+    plan_2d(&probe);
+    return probe.fuse2 ? 2 : 1;
+}
+
 int shll_create(shll_ctx **out, const shll_config *cfg)
 {
     if (!out || !cfg) return fail(nullptr, SHLL_E_INVAL, "shll_create: null argument");
@@ -286,8 +319,9 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     if (g.tform == SHLL_TFORM_AUTO) g.tform = (g.dims == 1 && g.order == 1) ? SHLL_TFORM_1D : SHLL_TFORM_2D;
     if (g.dims == 2) g.tform = SHLL_TFORM_2D;
     if (!(g.dt_on_dx > 0.0f) || (g.dims == 2 && !(g.dt_on_dy > 0.0f))) return fail(nullptr, SHLL_E_INVAL, "dt_on_dx / dt_on_dy must be positive");
-    if (g.halo_steps <= 0 || g.dims != 1 || g.nranks == 1) g.halo_steps = 1;
-    if (g.halo_steps * g.order > HALO1D_MAX || g.halo_steps * g.order > g.nx)
+    if (g.halo_steps <= 0 || g.nranks == 1) g.halo_steps = 1;
+    if (g.dims == 2 && g.halo_steps > 2) g.halo_steps = 2;  // 2D: 2 = two-step launches (1st-order FAST kernel), 2-row exchange
+    if (g.dims == 1 && (g.halo_steps * g.order > HALO1D_MAX || g.halo_steps * g.order > g.nx))
         return fail(nullptr, SHLL_E_INVAL, "halo_steps = %d: %d halo cells per side exceed the limit of %d or the slab's %d cells", g.halo_steps,
                     g.halo_steps * g.order, HALO1D_MAX, g.nx);
 
@@ -360,6 +394,11 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
             plan_2d(c, /*no_tma=*/true);
         }
     }
+    if (g.dims == 2 && g.nranks > 1 && g.halo_steps == 2 && !c->fuse2) {
+        int rc_ = fail(nullptr, SHLL_E_INVAL, "halo_steps = 2 needs the 2D 1st-order FAST kernel (ny %% 8 == 0, nx >= 8, SHLL_FUSE2 != 0)");
+        shll_destroy(c);
+        return rc_;
+    }
     if (g.dims == 2 && c->key.tma) {  // early-start flags, one per (chunk, tile) block of a step launch (step2d_tma.cuh)
         const size_t nflags = (size_t)c->ntiles * c->nchunks;
         CKC(cudaMalloc(&c->done, nflags * sizeof(unsigned)));
@@ -369,6 +408,7 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? (c->key.acc ? "_tma_acc" : "_tma") : ((g.dims == 1 && c->key.acc) ? "_acc" : ""),
              g.order, g.bc == SHLL_BC_REFLECT ? "reflect" : "outflow", g.order == 2 ? (g.limiter == SHLL_LIM_MC ? "mc_" : "minmod_") : "",
              g.mode == SHLL_MODE_STRICT ? "strict" : "fast", c->key.pow2 ? "pow2" : "gendt", c->key.vec, c->ntiles, c->nchunks);
+    if (c->fuse2) strncat(c->variant, "_x2", sizeof(c->variant) - strlen(c->variant) - 1);  // two time steps per launch
 #undef CKC
     *out = c;
     return SHLL_OK;
@@ -444,7 +484,7 @@ float *peer_halo_ptr(const shll_ctx *c, int side, int buf, int k)
     float *base = c->peer_state[side] + ((size_t)buf * c->ncomp + k) * pe + peer_interior_off(d);
     const long row = c->cfg.dims == 1 ? 1 : c->cfg.ny;
     if (side == 0) return base + (long)d.nx * row;
-    return base - (long)c->cfg.order * row;
+    return base - (long)(c->fuse2 ? 2 : c->cfg.order) * row;
 }
 
 bool multi(const shll_ctx *c) { return c->cfg.nranks > 1; }
@@ -473,7 +513,8 @@ int use_pdl(const shll_ctx *c)
     return ((!c->capturing || env_int("SHLL_PDL_GRAPH", 0) != 0) && env_int("SHLL_PDL", 1) != 0) ? 1 : 0;
 }
 
-int launch_one_step(shll_ctx *c)
+// nsub: time steps this launch advances (2: the two-step kernel of a fuse2 context)
+int launch_one_step(shll_ctx *c, int nsub = 1)
 {
     const shll_config &g = c->cfg;
     const int in = c->cur, outb = c->cur ^ 1;
@@ -482,8 +523,8 @@ int launch_one_step(shll_ctx *c)
     memset(&S, 0, sizeof(S));
     if (multi(c)) {
         S.enabled = 1;
-        S.want = c->state_index + 1;
-        S.post = c->state_index + 2;
+        S.want = c->state_index + 1;          // flag value = state index of the halo data + 1
+        S.post = c->state_index + nsub + 1;
         S.epoch = c->epoch + 1;
         S.wait_lo = lo_wall ? nullptr : c->flags + 0;
         S.wait_hi = hi_wall ? nullptr : c->flags + 1;
@@ -513,6 +554,7 @@ int launch_one_step(shll_ctx *c)
         P.half_dtdx = 0.5f * g.dt_on_dx; P.half_dtdy = 0.5f * g.dt_on_dy;
         P.alpha = g.alpha;
         P.quarter = 0.25f;
+        P.peer_depth = c->fuse2 ? 2 : g.order;
         S.edge_warps_lo = S.edge_warps_hi = (unsigned)c->ntiles;
         P.sync = S;
         const int warps = c->ntiles * c->nchunks;
@@ -533,7 +575,7 @@ int launch_one_step(shll_ctx *c)
             // STRICT 80.0 -> 86.8 / 42.4 -> 45.0.  Only on grids of at least 4 resident waves; launch-bound small grids keep the
             // plain wait.  SHLL_EARLY=2 forces it on, 0 off.
             const int early_mode = env_int("SHLL_EARLY", 1);
-            const int wave = c->sms * (g.order == 1 ? 16 : 12);             // resident one-warp blocks
+            const int wave = c->sms * ((g.order == 1 && !c->fuse2) ? 16 : 12);   // resident one-warp blocks
             const bool long_blocks = warps >= 4 * wave;
             if (T.pdl && c->done && (early_mode == 2 || (early_mode == 1 && long_blocks))) {
                 T.early_blocks = env_int("SHLL_EARLY_BLOCKS", wave * 3 / 2);
@@ -544,7 +586,9 @@ int launch_one_step(shll_ctx *c)
             }
             dim3 grid(warps);
             early2d = (T.done != nullptr);
-            if (c->key.acc) e = launch_step2d_acc(c->key, T, grid, c->tma_smem, c->stream);
+            T.early_diag = (nsub == 2) ? 1 : 0;
+            if (nsub == 2) e = launch_step2d_acc2(c->key, T, grid, c->tma_smem, c->stream);
+            else if (c->key.acc) e = launch_step2d_acc(c->key, T, grid, c->tma_smem, c->stream);
             else if (g.order == 1) e = launch_step2d_tma_o1(c->key, T, grid, c->tma_smem, c->stream);
             else if (g.mode == SHLL_MODE_STRICT) e = launch_step2d_tma_o2_strict(c->key, T, grid, c->tma_smem, c->stream);
             else e = launch_step2d_tma_o2_fast(c->key, T, grid, c->tma_smem, c->stream);
@@ -622,7 +666,7 @@ int launch_one_step(shll_ctx *c)
     if (e != cudaSuccess) return fail(c, SHLL_E_CUDA, "step kernel launch failed (%s): %s", c->variant, cudaGetErrorString(e));
     if (early2d) c->early_epoch++;
     c->cur = outb;
-    c->state_index++;
+    c->state_index += (unsigned)nsub;
     c->epoch++;
     c->launches++;
     if (sent) { c->round++; c->sends++; }
@@ -733,9 +777,10 @@ int shll_upload_u(shll_ctx *c, const float *const u[4])
                                                         c->round + 1);
         } else {
         const long row = g.ny;
-        const long count = (long)g.order * row;
+        const long depth = c->fuse2 ? 2 : g.order;
+        const long count = depth * row;
         const float *src_lo = c->plane(c->cur, 0);
-        const float *src_hi = c->plane(c->cur, 0) + ((long)g.nx - g.order) * row;
+        const float *src_hi = c->plane(c->cur, 0) + ((long)g.nx - depth) * row;
         float *dst_lo = lo_wall ? nullptr : peer_halo_ptr(c, 0, c->cur, 0);
         float *dst_hi = hi_wall ? nullptr : peer_halo_ptr(c, 1, c->cur, 0);
         push_halo_kernel<<<1, 1024, 0, c->stream>>>(src_lo, src_hi, dst_lo, dst_hi, count, c->ncomp, c->plane_elems,
@@ -815,7 +860,7 @@ int shll_run(shll_ctx *c, long nsteps)
         if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int crc = SHLL_OK;
             c->capturing = true;
-            for (int s = 0; s < GRAPH_STEPS && crc == SHLL_OK; s++) crc = launch_one_step(c);
+            for (int s = 0; s < GRAPH_STEPS && crc == SHLL_OK; s += c->fuse2 ? 2 : 1) crc = launch_one_step(c, c->fuse2 ? 2 : 1);
             c->capturing = false;
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             if (crc == SHLL_OK && e == cudaSuccess && g) {
@@ -834,13 +879,15 @@ int shll_run(shll_ctx *c, long nsteps)
         }
         while (nsteps >= GRAPH_STEPS) {
             CK(c, cudaGraphLaunch(c->graph, c->stream));
-            c->state_index += GRAPH_STEPS; c->epoch += GRAPH_STEPS; c->launches += GRAPH_STEPS;
+            c->state_index += GRAPH_STEPS; c->epoch += GRAPH_STEPS / (c->fuse2 ? 2 : 1); c->launches += GRAPH_STEPS / (c->fuse2 ? 2 : 1);
             nsteps -= GRAPH_STEPS;
         }
     }
-    for (long s = 0; s < nsteps; s++) {
-        rc = launch_one_step(c);
+    while (nsteps > 0) {
+        const int nsub = (c->fuse2 && nsteps >= 2) ? 2 : 1;
+        rc = launch_one_step(c, nsub);
         if (rc) return rc;
+        nsteps -= nsub;
     }
     return SHLL_OK;
 }

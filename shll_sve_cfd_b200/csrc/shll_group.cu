@@ -120,20 +120,8 @@ int shll_group_create(shll_group **out, const shll_config *cfg, int ngpus, const
         g->i0[r] = (int)(((long)r * cfg->nx) / ngpus);
         g->nx[r] = (int)(((long)(r + 1) * cfg->nx) / ngpus) - g->i0[r];
     }
-    // 1D: steps per halo exchange round (include/shll_b200.h: halo_steps) -- one value for the whole chain of slabs, from the
-    // smallest slab: K*order halo cells per side must fit into every slab and into the 32-cell mailboxes.  SHLL_HALO_K overrides
-    // the default of 16; a caller-supplied cfg->halo_steps is honoured (clamped the same way).
-    int halo_steps = 1;
-    if (cfg->dims == 1 && ngpus > 1) {
-        const char *e = getenv("SHLL_HALO_K");
-        halo_steps = cfg->halo_steps > 0 ? cfg->halo_steps : ((e && *e) ? atoi(e) : 16);
-        int smallest = g->nx[0];
-        for (int r = 1; r < ngpus; r++) smallest = g->nx[r] < smallest ? g->nx[r] : smallest;
-        const int order = cfg->order == 2 ? 2 : 1;
-        if (halo_steps > 32 / order) halo_steps = 32 / order;
-        if (halo_steps > smallest / order) halo_steps = smallest / order;
-        if (halo_steps < 1) halo_steps = 1;
-    }
+    // steps per halo exchange round (include/shll_b200.h: halo_steps) -- one value for the whole chain of slabs
+    const int halo_steps = shll_plan_halo_steps(cfg, ngpus);
     for (int r = 0; r < ngpus; r++) {
         shll_config c = *cfg;
         c.halo_steps = halo_steps;

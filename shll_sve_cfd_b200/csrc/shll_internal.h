@@ -45,6 +45,7 @@ cudaError_t launch_step2d_tma_o1(const KernelKey &k, const Step2DTmaParams &p, d
 cudaError_t launch_step2d_tma_o2_strict(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step2d_tma_o2_fast(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step2d_acc(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
+cudaError_t launch_step2d_acc2(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s);
 
 // Persistent register-resident 1D march (cooperative launch; grid = nblocks, one block per SM).

@@ -34,6 +34,8 @@ struct Step2DParams {
     int ntiles, nchunks;   // column tiles x row chunks = warps of the launch; chunks are balanced (sizes differ by <= 1)
     float dtdx, dtdy, half_dtdx, half_dtdy, alpha;
     float quarter;         // 0.25f, passed as a parameter so that it lives in a register (step2d_acc.cuh: one-LOP3 sign transfer)
+    int peer_depth;        // step2d_acc.cuh: rows per side stored into the neighbour slabs' halos (0 = the scheme's order; 2 for a
+                           // 1st-order context that also issues two-step launches, so that its halos are always two rows deep)
     HaloSync sync;         // multi-GPU only
 };
 

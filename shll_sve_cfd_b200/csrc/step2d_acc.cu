@@ -26,6 +26,14 @@ static cudaError_t go_o2(int cfg, const Step2DTmaParams &p, dim3 grid, size_t sm
     return cudaErrorInvalidValue;
 }
 
+// two 1st-order steps per launch (step2d_acc.cuh: step2d_acc2_kernel)
+cudaError_t launch_step2d_acc2(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
+{
+    if (k.mode != MODE_FAST || k.vec != 2 || k.order != 1) return cudaErrorInvalidValue;
+    if (k.bc == BC_REFLECT) return launch_pdl(step2d_acc2_kernel<BC_REFLECT, 12>, grid, dim3(32), smem, s, p.pdl != 0, p);
+    return launch_pdl(step2d_acc2_kernel<BC_OUTFLOW, 12>, grid, dim3(32), smem, s, p.pdl != 0, p);
+}
+
 cudaError_t launch_step2d_acc(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s)
 {
     if (k.mode != MODE_FAST || k.vec != 2) return cudaErrorInvalidValue;

@@ -446,8 +446,9 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
     X.r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
     const int never = -(1 << 30);
     X.wall_lo_row = X.wall_hi_row = X.first_real_row = X.last_real_row = never;  // (window-kernel fields, unused here)
-    X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? ORDER : 0;
-    X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - ORDER : 0x7fffffff;
+    const int depth = P.peer_depth > 0 ? P.peer_depth : ORDER;  // rows exchanged per side
+    X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? depth : 0;
+    X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - depth : 0x7fffffff;
     AccRows W;
     W.r0 = X.r0;
     W.r1 = X.r1;
@@ -460,10 +461,10 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
     W.quarter = P.quarter;
     W.nquarter = -P.quarter;
     W.stash = 0;
-    const bool touch_lo = (X.r0 < ORDER), touch_hi = (X.r1 > nx - ORDER);
+    const bool touch_lo = (X.r0 < depth), touch_hi = (X.r1 > nx - depth);
     if (P.sync.enabled) {
-        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
-        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
+        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo, 0);
+        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi, 1);
     }
 
     const int rbeg = X.r0 - ORDER;
@@ -498,6 +499,220 @@ __global__ void __launch_bounds__(32, MINB) step2d_acc_kernel(const __grid_const
     if (X.Y.tile_has_wall) acc_march<ORDER, BC, LIM, true, STASH, false>(X, W, rbeg, rlast, lane, tile);  // (few tiles: keep one code path)
     else if (T.tma_store) acc_march<ORDER, BC, LIM, false, STASH, true>(X, W, rbeg, rlast, lane, tile);
     else acc_march<ORDER, BC, LIM, false, STASH, false>(X, W, rbeg, rlast, lane, tile);
+
+    step2d_publish_output(T, tile, chunk, lane);
+    if (P.sync.enabled) {
+        if (touch_lo) halo_arrive(P.sync, P.sync.cnt_lo, P.sync.edge_warps_lo, P.sync.sig_lo);
+        if (touch_hi) halo_arrive(P.sync, P.sync.cnt_hi, P.sync.edge_warps_hi, P.sync.sig_hi);
+    }
+}
+
+// =========================================================================================================================
+// Two time steps per pass (order 1, FAST): step2d_acc2_kernel.
+//
+// The 1st-order kernel is not short of HBM bandwidth alone -- it waits on it (long-scoreboard stalls at the mbarriers) while
+// its issue slots are 55 % used.  Here a warp chains TWO steps in registers: stage A turns the rows of U^n arriving from the
+// ring into rows of U^(n+1) exactly as the one-step kernel does, and instead of storing them hands each finished row to stage B
+// -- the same row routine with its own carried state -- which finishes the rows of U^(n+2) that leave.  HBM sees one read and
+// one write per TWO steps; a row of U^(n+1) never exists in memory.  The lane layout needs no change: a halo lane holds two
+// cells, which is exactly the two-cell reach of two 1st-order steps (stage A is valid on 62 of the warp's 64 columns, stage B
+// on the 60 owned ones); a chunk reads two halo rows per side instead of one (the same redundancy per step).  Every row goes
+// through the same arithmetic as in the one-step kernel, so the results are bit-for-bit the ones of two one-step launches
+// (tests/test_gpu_fast_parity.py::test_fused_two_step_launches_give_the_bits_of_single_steps).
+//
+// One arriving row: returns which finished rows it produced -- bit 0: `lo` = row r-1, bit 1: `hi` = row r itself (r is the
+// physical wall row nx-1, whose Right flux is its own wall flux, base_shll_2d.c:168-171).
+template <int BC, bool WALLTILE, bool EDGE>
+__device__ __forceinline__ int acc1_advance(const YEdge<2> &Y, const Step2DParams &P, const AccRows &W, AccState<1> &S, int r,
+                                            float (&uin)[2][4], v2 (&lo)[4], v2 (&hi)[4])
+{
+    if (EDGE && (r < W.rmin || r > W.rmax)) return 0;
+    const v2 mdtdx = v2bc(-P.dtdx);
+    v2 fp[4], g[4], accN[4];
+    acc_row_y<1, BC, LIM_MINMOD, WALLTILE>(Y, P, W, uin, fp, g, accN);
+    if (EDGE && r == W.wall_lo_row) {  // Left of row 0 = its own wall flux (base_shll_2d.c:152-155)
+#pragma unroll
+        for (int k = 0; k < 4; k++) S.fpP[k] = ghost_fp_below<BC>(fp[k], g[k], k);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) lo[k] = v2fma(mdtdx, v2sub(S.D[k], g[k]), S.accB[k]);  // Right of row r-1 = F-[r] = -G[r]
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        S.D[k] = v2add(v2sub(fp[k], S.fpP[k]), g[k]);
+        S.accB[k] = accN[k];
+        S.fpP[k] = fp[k];
+    }
+    int made = 1;
+    if (EDGE && r == W.wall_hi_row) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) hi[k] = v2fma(mdtdx, v2sub(S.D[k], ghost_g_above<BC>(fp[k], g[k], k)), accN[k]);
+        made = 3;
+    }
+    return made;
+}
+
+__device__ __forceinline__ void acc_as_input(const v2 (&o)[4], float (&u)[2][4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) { u[0][k] = o[k].x; u[1][k] = o[k].y; }
+}
+
+template <int BC, bool WALLTILE, bool TSTORE, class Ctx>
+__device__ __forceinline__ void acc2_march(Ctx &X, const AccRows &W, int rbeg, int rlast, int lane, int tile)
+{
+    AccState<1> SA, SB;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        SA.fpP[k] = SA.D[k] = SA.accB[k] = SA.gP[k] = SA.ep[k] = SA.em[k] = SA.PhiP[k] = SA.acc0[k] = v2bc(0.0f);
+        SB.fpP[k] = SB.D[k] = SB.accB[k] = SB.gP[k] = SB.ep[k] = SB.em[k] = SB.PhiP[k] = SB.acc0[k] = v2bc(0.0f);
+    }
+    const Step2DParams &P = *X.P;
+    const int nx = P.nx;
+    // first row of U^(n+1) stage A can make: the row after its first input row -- or row 0 itself at a physical wall (ghost flux)
+    const int a0 = (P.lo_wall && rbeg <= 0) ? 0 : rbeg + 1;
+    // ... and the first row of U^(n+2) stage B can make, by the same rule applied to the rows it receives
+    const int b0 = (P.lo_wall && a0 == 0) ? 0 : a0 + 1;
+    int stage = 0;
+    uint32_t parity = 0;
+    float uin[2][4], umid[2][4];
+    v2 oA[4], oA2[4], oB[4], oB2[4];
+    bool store_pending = false;
+    // stage B: row i of U^(n+1) arrives; rows of U^(n+2) inside [r0, r1) leave (EDGE form)
+    auto feed_b = [&](int i, const v2(&mid)[4]) {
+        acc_as_input(mid, umid);
+        const int made = acc1_advance<BC, WALLTILE, true>(X.Y, P, W, SB, i, umid, oB, oB2);
+        if ((made & 1) && i - 1 >= b0 && i - 1 >= W.r0 && i - 1 < W.r1) acc_store(X, i - 1, oB);
+        if ((made & 2) && i < W.r1) acc_store(X, i, oB2);
+    };
+    for (int box = 0; box < X.nboxes; box++) {
+        const int r = rbeg + 4 * box;
+        mbar_wait(X.bars + 8u * stage, parity);
+        const int ifirst = r - 2;  // rows of U^(n+2) finished by this box: ifirst .. ifirst + 3
+        const bool edge = (P.lo_wall && r <= 1) || (P.hi_wall && r + 3 >= nx - 1) || (r + 3 > rlast) || (ifirst < W.r0) || (ifirst + 3 >= W.r1) ||
+                          (ifirst < X.peer_lo_end) || (ifirst + 3 >= X.peer_hi_begin);
+        if (edge) {
+#pragma unroll 1
+            for (int w = 0; w < 4; w++) {
+                const int rr = r + w;
+                if (rr > rlast) break;
+                acc_read_row(X, stage, w, uin);
+                const int made = acc1_advance<BC, WALLTILE, true>(X.Y, P, W, SA, rr, uin, oA, oA2);
+                if ((made & 1) && rr - 1 >= a0) feed_b(rr - 1, oA);
+                if (made & 2) feed_b(rr, oA2);
+            }
+            __syncwarp();
+            if (lane == 0 && box + X.stages < X.nboxes) X.arm(box + X.stages, stage);
+        } else {
+            if (TSTORE) {
+                if (store_pending) {
+                    if (lane == 0) tma_store_wait_read();
+                    __syncwarp();
+                }
+            }
+#define SHLL_ACC2_ROW(WI)                                                                               \
+            X.template read_row<WI>(stage, uin);                                                        \
+            acc1_advance<BC, WALLTILE, false>(X.Y, P, W, SA, r + WI, uin, oA, oA2);                     \
+            acc_as_input(oA, umid);                                                                     \
+            acc1_advance<BC, WALLTILE, false>(X.Y, P, W, SB, r + WI - 1, umid, oB, oB2);                \
+            if (TSTORE) acc_stage_row<WI>(W, oB); else acc_store_owned(X, r + WI - 2, oB);
+            SHLL_ACC2_ROW(0)
+            SHLL_ACC2_ROW(1)
+            SHLL_ACC2_ROW(2)
+            SHLL_ACC2_ROW(3)
+#undef SHLL_ACC2_ROW
+            if (TSTORE) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) {
+                if (TSTORE) tma_store_3d(&X.T->tmap_out, tile * (int)ACC_OUT_COLS, ifirst + 2, 0, W.sstage_base);
+                if (box + X.stages < X.nboxes) X.arm(box + X.stages, stage);
+            }
+            store_pending = TSTORE;
+        }
+        stage++;
+        if (stage == X.stages) { stage = 0; parity ^= 1u; }
+    }
+    if (TSTORE && lane == 0) tma_store_wait_all();
+}
+
+template <int BC, int MINB>
+__global__ void __launch_bounds__(32, MINB) step2d_acc2_kernel(const __grid_constant__ Step2DTmaParams T)
+{
+    constexpr int R = 4, VEC = 2, HL = 1, DEPTH = 2;  // DEPTH: halo rows per side = steps per pass
+    constexpr int USEFUL = (32 - 2 * HL) * VEC;
+    extern __shared__ __align__(128) unsigned char smem[];
+    const Step2DParams &P = T.base;
+    const int lane = threadIdx.x;
+    const int gw = blockIdx.x;
+    const int tile = gw % P.ntiles;
+    int chunk = gw / P.ntiles;
+    if (P.nchunks > 2) chunk = (chunk == 0) ? 0 : (chunk == 1 ? P.nchunks - 1 : chunk - 1);  // edge chunks first
+
+    TmaCtx<VEC, R> X;
+    X.P = &P;
+    X.T = &T;
+    const int nx = P.nx;
+    X.ny = P.ny;
+    const int xs = tile * USEFUL - HL * VEC;
+    X.x0 = xs & ~3;
+    X.j0 = xs + lane * VEC;
+    X.owner = (lane >= HL) && (lane < 32 - HL) && (X.j0 < X.ny);
+    X.Y.tile_has_wall = (tile == 0) || (tile == P.ntiles - 1);
+    X.Y.ghost_lo = (X.j0 + VEC - 1 == -1);
+    X.Y.ghost_hi = (X.j0 == X.ny);
+#pragma unroll
+    for (int v = 0; v < VEC; v++) {
+        X.Y.y_inner[v] = (X.j0 + v > 0 && X.j0 + v < X.ny - 1);
+        X.Y.outside[v] = (X.j0 + v < 0 || X.j0 + v >= X.ny);
+    }
+    X.r0 = (int)(((long)chunk * nx) / P.nchunks);
+    X.r1 = (int)(((long)(chunk + 1) * nx) / P.nchunks);
+    const int never = -(1 << 30);
+    X.wall_lo_row = X.wall_hi_row = X.first_real_row = X.last_real_row = never;
+    X.peer_lo_end = (P.sync.enabled && P.lo_peer[0] != nullptr) ? DEPTH : 0;
+    X.peer_hi_begin = (P.sync.enabled && P.hi_peer[0] != nullptr) ? nx - DEPTH : 0x7fffffff;
+    AccRows W;
+    W.r0 = X.r0;
+    W.r1 = X.r1;
+    W.rmin = P.lo_wall ? 0 : -2;
+    W.rmax = P.hi_wall ? nx - 1 : nx + 1;
+    W.wall_lo_row = P.lo_wall ? 0 : never;
+    W.wall_hi_row = P.hi_wall ? nx - 1 : never;
+    W.noslope_lo = never;
+    W.noslope_hi = -never;
+    W.quarter = P.quarter;
+    W.nquarter = -P.quarter;
+    W.stash = 0;
+    const bool touch_lo = (X.r0 < DEPTH), touch_hi = (X.r1 > nx - DEPTH);
+    if (P.sync.enabled) {
+        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo, 0);
+        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi, 1);
+    }
+    const int rbeg = X.r0 - DEPTH;
+    const int rlast = X.r1 - 1 + DEPTH;
+    X.stages = T.stages;
+    X.ring = smem_u32(smem);
+    X.bars = X.ring + TmaCtx<VEC, R>::STAGE_STRIDE * X.stages;
+    X.lane_off = (uint32_t)(xs - X.x0 + lane * VEC) * 4u;
+    X.ybase = rbeg + 2;
+    X.nboxes = (rlast - rbeg) / R + 1;
+    const uint32_t smem_top = X.bars + 8u * X.stages;
+    W.sstage_base = (smem_top + 127u) & ~127u;
+    W.sstage = W.sstage_base + 8u * (uint32_t)(lane - HL);
+    W.stager = (lane >= HL) && (lane < 32 - HL);
+    if (lane == 0) {
+        for (int s = 0; s < X.stages; s++) mbar_init(X.bars + 8u * s, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    step2d_wait_for_input(T, tile, chunk, lane);
+    if (lane == 0) {
+        for (int b = 0; b < X.stages && b < X.nboxes; b++) X.arm(b, b);
+    }
+    __syncwarp();
+
+    if (X.Y.tile_has_wall) acc2_march<BC, true, false>(X, W, rbeg, rlast, lane, tile);
+    else if (T.tma_store) acc2_march<BC, false, true>(X, W, rbeg, rlast, lane, tile);
+    else acc2_march<BC, false, false>(X, W, rbeg, rlast, lane, tile);
 
     step2d_publish_output(T, tile, chunk, lane);
     if (P.sync.enabled) {

@@ -38,6 +38,7 @@ struct Step2DTmaParams {
     unsigned early_want, early_post;
     unsigned *done;       // [nchunks * ntiles]
     unsigned *early_err;
+    int early_diag;       // also wait for the four diagonal neighbours (two-step launches: the footprint of two cross stencils is a diamond)
     const CUtensorMap *tmap_global;  // optional copy of the same descriptor in device memory (debug switch SHLL_TMAP_GLOBAL)
     int stages;
     int pdl;              // launched with programmatic stream serialization: the kernel waits for its predecessor itself (halo_sync.cuh)
@@ -92,9 +93,10 @@ __device__ __forceinline__ void step2d_wait_for_input(const Step2DTmaParams &T, 
     const bool last_chunk_slot = T.base.nchunks > 2 && (int)blockIdx.x >= T.base.ntiles && (int)blockIdx.x < 2 * T.base.ntiles;
     if ((int)blockIdx.x < T.early_blocks && !last_chunk_slot) {
         const Step2DParams &P = T.base;
-        if (lane < 5) {
-            // lane 0: own block; 1, 2: tile -+ 1; 3, 4: chunk -+ 1
-            const int dt = (lane == 1) ? -1 : (lane == 2 ? 1 : 0), dc = (lane == 3) ? -1 : (lane == 4 ? 1 : 0);
+        if (lane < (T.early_diag ? 9 : 5)) {
+            // lane 0: own block; 1, 2: tile -+ 1; 3, 4: chunk -+ 1; 5..8: the diagonals
+            const int dt = (lane == 1 || lane == 5 || lane == 7) ? -1 : ((lane == 2 || lane == 6 || lane == 8) ? 1 : 0);
+            const int dc = (lane == 3 || lane == 5 || lane == 6) ? -1 : ((lane == 4 || lane == 7 || lane == 8) ? 1 : 0);
             const int t = tile + dt, c = chunk + dc;
             if (t >= 0 && t < P.ntiles && c >= 0 && c < P.nchunks) {
                 const unsigned *f = T.done + (size_t)c * P.ntiles + t;
@@ -121,7 +123,7 @@ __device__ __forceinline__ void step2d_wait_for_input(const Step2DTmaParams &T, 
 __device__ __forceinline__ void step2d_publish_output(const Step2DTmaParams &T, int tile, int chunk, int lane)
 {
     // publishers: every block an early block of the next launch may depend on (its own launch slot, tile +-1, chunk +-1)
-    if (T.done != nullptr && (int)blockIdx.x < T.early_blocks + T.base.ntiles + 1) {
+    if (T.done != nullptr && (int)blockIdx.x < T.early_blocks + T.base.ntiles + 2) {
         __syncwarp();
         if (lane == 0) {
             asm volatile("fence.proxy.async;" ::: "memory");

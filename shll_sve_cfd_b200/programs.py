@@ -208,15 +208,12 @@ def save_results(pb: Problem, p: np.ndarray, path: str) -> None:
                     c += 1
 
 
-def halo_steps_for(pb: Problem, nranks: int, want: int | None = None) -> int:
-    """K of the 1D temporal halo blocking (include/shll_b200.h: shll_config.halo_steps) for a domain of pb.nx cells cut into
-    nranks balanced slabs: the same value on every rank, K*order <= 32 and <= the smallest slab.  SHLL_HALO_K overrides 16."""
-    import os
-    if pb.dims != 1 or nranks <= 1:
+def halo_steps_for(pb: Problem, nranks: int, mode: int = capi.MODE_STRICT) -> int:
+    """shll_config.halo_steps for a domain of pb.nx rows / cells cut into nranks balanced slabs (include/shll_b200.h:
+    shll_plan_halo_steps): the same value on every rank."""
+    if nranks <= 1:
         return 1
-    k = want if want is not None else int(os.environ.get("SHLL_HALO_K", "16"))
-    smallest = pb.nx // nranks
-    return max(1, min(k, 32 // pb.order, smallest // pb.order))
+    return capi.plan_halo_steps(pb.dims, pb.nx, pb.ny, pb.order, mode, nranks, bc=pb.bc, limiter=pb.limiter)
 
 
 def make_solver(pb: Problem, mode: int = capi.MODE_STRICT, device: int = 0, rank: int = 0, nranks: int = 1,

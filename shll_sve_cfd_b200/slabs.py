@@ -71,7 +71,7 @@ class SlabSolver:
         self.dist = dist
         self.slab = partition(pb.nx, nranks, rank)
         # 1D: K steps per halo exchange round, agreed from the GLOBAL problem so that every rank uses the same value
-        self.halo_steps = programs.halo_steps_for(pb, nranks)
+        self.halo_steps = programs.halo_steps_for(pb, nranks, mode) if solver_factory is None else 1
         factory = solver_factory or (lambda pb_, mode_, dev_, r_, n_, nl_: programs.make_solver(
             pb_, mode_, device=dev_, rank=r_, nranks=n_, nx_local=nl_, halo_steps=self.halo_steps))
         self.solver = factory(pb, mode, device, rank, nranks, self.slab.nx_local)

@@ -77,11 +77,11 @@ def test_reference_arm_other_ranks_do_nothing():
 def test_b200_arm_line_small_grid():
     d = _run(["--workload", "2d_o1", "--nx", "512", "--ny", "512", "--steps", "40", "--warmup", "3"], {"SHLL_BENCH_CPU_BUDGET": "0.05"})
     assert BASE_KEYS | {"roofline", "gpu_launches", "clocks", "other_mode"} <= set(d)
-    assert d["gpu_launches"] == 40 and d["steps"] == 40 and d["n_gpus"] == 1 and d["dtype"] == "f32"
+    assert d["gpu_launches"] == 20 and d["steps"] == 40 and d["n_gpus"] == 1 and d["dtype"] == "f32"   # two steps per launch
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["peak"] > 1000
     assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["algorithmic_bytes_per_launch"] == 32 * 512 * 512
+    assert r["algorithmic_bytes_per_launch"] == 2 * 32 * 512 * 512 and r["steps_per_launch"] == 2
     assert abs(d["value"] - 512 * 512 * 40 / (d["ms_per_step"] * 40e-3)) / d["value"] < 1e-6
     e = d["e2e"]
     assert e["value"] > 0 and e["value"] < d["value"] and e["h2d_bytes_per_step"] == pytest.approx(4 * 4 * 512 * 512 / 40)

@@ -46,14 +46,14 @@ def _fast_run(pb, u0, steps, variant=0):
 
 @pytest.mark.parametrize("steps", [10, 40])
 def test_fast_4096x4096_benched_geometry_window_vs_oracle(steps, oracle):
-    """configs[2] exactly as bench.py runs it: step2d_acc, 60-column tiles, 18-row chunks (228 chunks), FAST."""
+    """configs[2] exactly as bench.py runs it: step2d_acc2 (two steps per launch), 60-column tiles, 44-row chunks (94 chunks), FAST."""
     n, W = 4096, 192
     pb = programs.BASE_SHLL_2D.resized(n, n)
     i0 = j0 = int(0.2 * n) - W // 2                      # straddles the corner of the low-density box
     u0 = programs.cons_from_prim(pb, programs.initial_primitives(pb)).reshape(4, n, n)
     got, name, launches = _fast_run(pb, u0.reshape(4, -1), steps)
-    assert "_tma_acc" in name and "chunks228" in name and "fast" in name, name
-    assert launches == steps
+    assert "_tma_acc" in name and "chunks94" in name and "fast" in name and name.endswith("_x2"), name
+    assert launches == steps // 2
     got = got.reshape(4, n, n)
     sub = programs.Problem("w", 2, W, W, order=1, bc=capi.BC_OUTFLOW, ic="implosion")
     ref = oracle.run(oracle_cfg_for(oracle, sub, nthreads=8), np.ascontiguousarray(u0[:, i0:i0 + W, j0:j0 + W]).reshape(4, -1), steps).reshape(4, W, W)
@@ -62,8 +62,8 @@ def test_fast_4096x4096_benched_geometry_window_vs_oracle(steps, oracle):
     b = np.ascontiguousarray(ref[:, m:W - m, m:W - m]).reshape(4, -1)
     rel, absmax = _prim_err(sub, a, b)
     assert rel <= FAST_TOL_DEFAULT, f"{name}: {rel:.3e} (abs {absmax:.3e}) after {steps} steps"
-    # the window spans chunk seams (rows 18k) and tile seams (columns 60k) of the benched geometry
-    assert (i0 + m) // 18 != (i0 + W - m) // 18 and (j0 + m) // 60 != (j0 + W - m) // 60
+    # the window spans chunk seams (every ~43.6 rows: rows 741, 784, 828, 871 lie inside) and tile seams (columns 60k) of the benched geometry
+    assert (i0 + m) * 94 // n != (i0 + W - m) * 94 // n and (j0 + m) // 60 != (j0 + W - m) // 60
     # far from the density jump the gas is at rest and must stay bit-for-bit at rest
     assert np.array_equal(bits(got[:, 2000:2100, 2000:2100]), bits(u0[:, 2000:2100, 2000:2100]))
 
@@ -162,6 +162,47 @@ def test_fast_random_state_all_scheme_combinations(scheme, oracle):
     ref = oracle.run(oracle_cfg_for(oracle, pb, nthreads=4), u0, 25)
     rel, absmax = _prim_err(pb, got, ref)
     assert rel <= FAST_TOL_DEFAULT, f"{scheme} ({name}): {rel:.3e} (abs {absmax:.3e})"
+
+
+@pytest.mark.parametrize("shape", [(64, 128), (41, 128), (130, 192), (257, 64), (96, 248)], ids=lambda s: f"{s[0]}x{s[1]}")
+@pytest.mark.parametrize("bc", ["reflect", "outflow"])
+def test_fused_two_step_launches_give_the_bits_of_single_steps(shape, bc, monkeypatch):
+    """The 1st-order FAST kernel advances two steps per launch (csrc/step2d_acc.cuh: step2d_acc2_kernel): stage A's rows of
+    U^(n+1) go to stage B in registers.  Same bits as one launch per step -- walls, ragged last tile, thin / uneven chunks, odd
+    step counts (the last step is a one-step launch), split runs -- and through slabs sharing a device (two-row halo exchange)."""
+    pb = replace(programs.Problem("x", 2, shape[0], shape[1], order=1, bc=capi.BC_REFLECT if bc == "reflect" else capi.BC_OUTFLOW,
+                                  ic="implosion"), lx=shape[0] / shape[1])
+    u0 = _random_state(pb, seed=shape[0] + shape[1])
+    monkeypatch.setenv("SHLL_GRAPH", "0")
+    outs = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("SHLL_FUSE2", fuse)
+        for rpc in ("-", "5", "8", "1000"):
+            if rpc == "-":
+                monkeypatch.delenv("SHLL_ROWS_PER_CHUNK", raising=False)
+            else:
+                monkeypatch.setenv("SHLL_ROWS_PER_CHUNK", rpc)
+            with programs.make_solver(pb, capi.MODE_FAST) as s:
+                s.upload_u(u0)
+                s.run(7); s.run(2); s.run(1); s.run(12)
+                outs[(fuse, rpc)] = (s.download_u(), s.variant, s.launches)
+    base = outs[("0", "-")]
+    assert not base[1].endswith("_x2") and base[2] == 22
+    for key, (u, name, launches) in outs.items():
+        assert np.array_equal(bits(u), bits(base[0])), f"{key} {name} differs from one launch per step"
+        if key[0] == "1":
+            assert name.endswith("_x2") and launches == 4 + 1 + 1 + 6, (name, launches)
+    # slabs on one device: halo_steps = 2 chosen by the group front end when every slab is at least 16 rows
+    if shape[0] >= 48:
+        monkeypatch.setenv("SHLL_FUSE2", "1")
+        monkeypatch.delenv("SHLL_ROWS_PER_CHUNK", raising=False)
+        _, _, _, dtdx, dtdy = programs.time_constants(pb)
+        with capi.Group(2, pb.nx, pb.ny, ngpus=3, devices=[0, 0, 0], order=1, bc=pb.bc, mode=capi.MODE_FAST, dt_on_dx=float(dtdx),
+                        dt_on_dy=float(dtdy)) as g:
+            g.upload_u(u0)
+            g.run(7); g.run(2); g.run(1); g.run(12)
+            assert g.variant(0).endswith("_x2"), g.variant(0)
+            assert np.array_equal(bits(g.download_u()), bits(base[0])), "3 slabs with two-step launches differ from one slab"
 
 
 # ------------------------------------------------------------------------------------ full-length FAST runs

@@ -90,7 +90,7 @@ def test_group_on_one_device_is_bitwise_the_single_slab_run(case, devices, manif
             assert np.array_equal(bits(got_p), bits(want_p)) and np.array_equal(bits(got_a), bits(want_a))
             assert g.max_cfl() == want_cfl
             np.testing.assert_allclose(g.conserved_sums(), want_sums, rtol=1e-12, atol=1e-9)
-            assert g.launches >= steps * len(devices) or pb.dims == 1
+            assert g.launches >= steps * len(devices) // 2 or pb.dims == 1    # (two steps per launch in 2D 1st-order FAST)
         if mode == capi.MODE_STRICT and steps == load_golden(case)[2]:
             assert np.array_equal(bits(got_u), bits(gu)), f"{case}: differs from the reference fixture"
 
