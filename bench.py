@@ -645,7 +645,11 @@ def main():
             "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s", "frac": r["achieved"] / r["peak"],
                          "traffic": tr, "traffic_source": tr_src, "peak_source": r["peak_src"],
                          "algorithmic_bytes_per_launch": r["bytes_per_launch"] * (K // max(1, r["launches"])),
-                         "steps_per_launch": K // max(1, r["launches"]), "kernel": r["variant"]},
+                         "steps_per_launch": K // max(1, r["launches"]), "kernel": r["variant"],
+                         **({"note": "two time steps per launch (U^(n+1) never leaves the registers): the DRAM traffic of a launch is one read + one "
+                                     "write of the state, i.e. half the algorithmic 32 B per cell-update, so frac (algorithmic bytes / measured copy "
+                                     "peak) can exceed 1; against the traffic actually moved the launch runs at traffic / launch time"}
+                            if r["variant"].endswith("_x2") else {})},
             "clocks": r["clocks"],
             "parity_vs_1gpu": r.get("parity_vs_1gpu"),
             "halo_exchange": r.get("halo"),
