@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libshll_b200.so")
-SOURCES = ["shll_capi.cu", "shll_group.cu", "step1d.cu", "step2d_o1.cu", "step2d_o2_strict.cu", "step2d_o2_fast.cu", "step2d_acc.cu", "selftest.cu"]
+SOURCES = ["shll_capi.cu", "shll_group.cu", "step1d.cu", "step2d_o1.cu", "step2d_o2_strict.cu", "step2d_o2_fast.cu", "step2d_acc.cu", "step2d_acc_o2.cu", "selftest.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -fmad=false: contraction is never left to the compiler (STRICT must not fuse; FAST fuses explicitly with __fmaf_rn).
 # -ftz=false -prec-div=true -prec-sqrt=true are the defaults, spelled out because STRICT mode depends on them.

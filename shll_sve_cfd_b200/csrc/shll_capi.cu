@@ -154,8 +154,7 @@ void plan_2d(shll_ctx *c, bool no_tma = false)
     c->key.vec = vec;
     // FAST arithmetic, 2 cells per lane: the face-flux accumulate kernel (step2d_acc.cuh); SHLL_ACC=0 keeps the window kernel.
     c->key.acc = c->key.tma && vec == 2 && g.mode == SHLL_MODE_FAST && env_int("SHLL_ACC", 1) != 0;
-    c->key.acc_cfg = env_int("SHLL_ACC_CFG", 1);
-    if (c->key.acc_cfg < 0 || c->key.acc_cfg > 7) c->key.acc_cfg = 1;
+    c->key.acc_cfg = 1;  // (round-1/2 register-cap and stash experiments: only the winning variant is instantiated, step2d_acc_o2.cu)
     // two steps per launch (step2d_acc.cuh: step2d_acc2_kernel): single slab -> decided here; slabs -> only when the front end asked
     // for it on EVERY slab (halo_steps = 2), because neighbouring slabs must issue the same sequence of launches
     c->fuse2 = c->key.acc && g.order == 1 && g.nx >= 8 && env_int("SHLL_FUSE2", 1) != 0 && (g.nranks == 1 || g.halo_steps == 2);
@@ -235,8 +234,6 @@ int make_tensor_maps(shll_ctx *c)
     if (c->tma_stages > 16) c->tma_stages = 16;
     const size_t stage_stride = ((size_t)4 * R * (32 * c->key.vec + 4) * 4 + 127) & ~(size_t)127;
     c->tma_smem = (size_t)c->tma_stages * stage_stride + 8 * c->tma_stages;
-    if (c->key.acc && g.order == 2 && (c->key.acc_cfg == 2 || c->key.acc_cfg == 3 || c->key.acc_cfg == 4))
-        c->tma_smem += (c->key.acc_cfg == 4 ? 2048 : 4096) + 16;  // per-warp stash (step2d_acc.cuh)
     if (c->tma_store) c->tma_smem += 3840 + 128;                   // per-warp store stage (step2d_acc.cuh: ACC_OUT_STAGE_BYTES)
     return 0;
 }
