@@ -650,6 +650,8 @@ int launch_one_step(shll_ctx *c, int nsub = 1)
         const int grid_real = ((ntiles_real + P.tiles_per_warp - 1) / P.tiles_per_warp + 3) / 4;
         if (P.pdl && c->done && grid_real >= 6 && env_int("SHLL_EARLY", 1) != 0) {
             P.early_blocks = (int)grid.x - 1 < EARLY_MAX ? (int)grid.x - 1 : EARLY_MAX;
+            const int cap = env_int("SHLL_EARLY_BLOCKS", EARLY_MAX);
+            if (cap >= 1 && cap < P.early_blocks) P.early_blocks = cap;
             P.early_want = c->early_epoch;
             P.early_post = c->early_epoch + 1;
             P.early_prev_grid = c->early_prev_grid;

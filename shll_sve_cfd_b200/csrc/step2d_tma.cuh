@@ -122,8 +122,9 @@ __device__ __forceinline__ void step2d_wait_for_input(const Step2DTmaParams &T, 
 // End of a 2D step block: every lane's stores (and lane 0's TMA stores, already waited for) are issued.
 __device__ __forceinline__ void step2d_publish_output(const Step2DTmaParams &T, int tile, int chunk, int lane)
 {
-    // publishers: every block an early block of the next launch may depend on (its own launch slot, tile +-1, chunk +-1)
-    if (T.done != nullptr && (int)blockIdx.x < T.early_blocks + T.base.ntiles + 2) {
+    // publishers: every block an early block of the next launch may depend on (its own launch slot, tile +-1, chunk +-1).  In launch
+    // order (chunk 0, the last chunk, 1, 2, ...) chunk 0's upper neighbour sits TWO chunk slots further, every other one ONE.
+    if (T.done != nullptr && (int)blockIdx.x < T.early_blocks + 2 * T.base.ntiles + 2) {
         __syncwarp();
         if (lane == 0) {
             asm volatile("fence.proxy.async;" ::: "memory");

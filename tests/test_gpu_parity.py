@@ -424,3 +424,30 @@ def test_config1_65536_cells_run_to_completion_is_bit_exact():
     assert l1 <= FAST_LONG_1D_MEAN_TOL, l1
     for level, most in FAST_LONG_1D_SHARE_ABOVE.items():
         assert float((e > level).mean()) <= most, (level, float((e > level).mean()))
+
+
+@pytest.mark.parametrize("early_blocks", [1, 8, 40, 100000])
+def test_early_start_of_the_first_wave_any_size_of_the_wave_same_bits(early_blocks, monkeypatch):
+    """The blocks of a launch's first wave start on the flags of the blocks of the previous launch they depend on instead of
+    griddepcontrol.wait (csrc/step2d_tma.cuh, csrc/step1d.cuh).  Forced on small grids with every size of the early set --
+    smaller than a row of tiles, a few chunk rows, the whole grid: same bits as the plain wait, and no flag is ever waited for
+    that nobody publishes (a missing publisher would show as the 2 s poll timeout -> SHLL_E_TIMEOUT)."""
+    import time
+    monkeypatch.setenv("SHLL_GRAPH", "0")
+    monkeypatch.setenv("SHLL_PERSIST", "0")
+    cases = [replace(programs.BASE_SHLL_2D.resized(96, 512), lx=96 / 512), replace(programs.SECOND_ORDER_2D.resized(96, 512), lx=96 / 512),
+             programs.SECOND_ORDER_1D.resized(200000)]
+    for pb in cases:
+        u0 = _random_state(pb, seed=early_blocks % 97)
+        for mode in (capi.MODE_STRICT, capi.MODE_FAST):
+            outs = []
+            for early in ("0", "2"):
+                monkeypatch.setenv("SHLL_EARLY", early)
+                monkeypatch.setenv("SHLL_EARLY_BLOCKS", str(early_blocks))
+                t0 = time.perf_counter()
+                with programs.make_solver(pb, mode) as s:
+                    s.upload_u(u0)
+                    s.run(21)
+                    outs.append(s.download_u())
+                assert time.perf_counter() - t0 < 1.5, f"{pb.name} early={early}: a block waited for a flag nobody publishes"
+            assert np.array_equal(bits(outs[0]), bits(outs[1])), f"{pb.name} mode {mode} early_blocks {early_blocks}"
