@@ -74,6 +74,7 @@ struct shll_ctx {
     int early_prev_grid;   // ... and its grid size
     int sms;               // multiprocessors of the device
     bool fuse2;            // 2D FAST 1st order: two steps per launch (step2d_acc2_kernel) whenever at least two steps remain
+    bool fuse1d;           // 1D FAST 2nd order: two steps per launch (step1d_acc2_kernel)
     KernelKey key;
     int ntiles, nchunks;
     CUtensorMap tmap[2];   // 2D TMA kernels: one 3D map {ny, nx+4, 4} per ping-pong buffer
@@ -243,6 +244,8 @@ void plan_1d(shll_ctx *c)
     c->key.vec = 4;
     c->key.acc = c->cfg.mode == SHLL_MODE_FAST && c->cfg.order == 2 && env_int("SHLL_ACC", 1) != 0;
     c->key.acc_cfg = env_int("SHLL_ACC_CFG", 0);
+    // two steps per launch (step1d_acc.cuh): slabs need an even number of steps per exchange round so that a launch never straddles one
+    c->fuse1d = c->key.acc && env_int("SHLL_FUSE1D", 1) != 0 && (c->cfg.nranks == 1 || c->cfg.halo_steps % 2 == 0);
     c->ntiles = (c->cfg.nx + 119) / 120;
     c->nchunks = 1;
 }
@@ -405,7 +408,7 @@ int shll_create(shll_ctx **out, const shll_config *cfg)
     snprintf(c->variant, sizeof(c->variant), "step%dd%s_o%d_%s_%s%s_%s_vec%d_tiles%d_chunks%d", g.dims, (g.dims == 2 && c->key.tma) ? (c->key.acc ? "_tma_acc" : "_tma") : ((g.dims == 1 && c->key.acc) ? "_acc" : ""),
              g.order, g.bc == SHLL_BC_REFLECT ? "reflect" : "outflow", g.order == 2 ? (g.limiter == SHLL_LIM_MC ? "mc_" : "minmod_") : "",
              g.mode == SHLL_MODE_STRICT ? "strict" : "fast", c->key.pow2 ? "pow2" : "gendt", c->key.vec, c->ntiles, c->nchunks);
-    if (c->fuse2) strncat(c->variant, "_x2", sizeof(c->variant) - strlen(c->variant) - 1);  // two time steps per launch
+    if (c->fuse2 || c->fuse1d) strncat(c->variant, "_x2", sizeof(c->variant) - strlen(c->variant) - 1);  // two time steps per launch
 #undef CKC
     *out = c;
     return SHLL_OK;
@@ -602,8 +605,10 @@ int launch_one_step(shll_ctx *c, int nsub = 1)
         const bool m = multi(c);
         const int K = m ? c->halo_K : 1, H = K * g.order;
         const int pos = m ? (int)((c->state_index - c->origin) % (unsigned)K) : 0;
-        const bool recv = m && pos == 0, send = m && pos == K - 1;
-        const int ext = (!m || send) ? 0 : (int)round_up((size_t)(H - g.order * (pos + 1)), 4);  // halo cells this step still updates
+        const bool recv = m && pos == 0, send = m && pos + nsub - 1 == K - 1;
+        // halo cells this launch still updates: the range of its FIRST step (a two-step launch stores the same range; what lies
+        // outside the second step's range is garbage that no later step of the round reads)
+        const int ext = (!m || H - g.order * (pos + 1) <= 0) ? 0 : (int)round_up((size_t)(H - g.order * (pos + 1)), 4);
         const int ext_lo = lo_wall ? 0 : ext, ext_hi = hi_wall ? 0 : ext;
         for (int k = 0; k < 3; k++) {
             P.in[k] = c->plane(in, k) - ext_lo;
@@ -622,7 +627,7 @@ int launch_one_step(shll_ctx *c, int nsub = 1)
         P.mail_hi = (recv && !hi_wall) ? reinterpret_cast<const float *>(c->flags + mail_index(1, c->round, 0)) : nullptr;
         P.interior_end = P.n;
         if (recv && !hi_wall && ext_lo + g.nx < P.interior_end) P.interior_end = ext_lo + g.nx;  // tiles reading the upper halo cells
-        if (send && !hi_wall && g.nx - H < P.interior_end) P.interior_end = g.nx - H;           // tiles owning cells to be sent
+        if (send && !hi_wall && g.nx - H + ext_lo < P.interior_end) P.interior_end = g.nx - H + ext_lo;  // tiles owning cells to be sent
         P.lo_wall = lo_wall; P.hi_wall = hi_wall;
         P.ntiles = (P.n + 119) / 120;
         P.dtdx = g.dt_on_dx; P.half_dtdx = 0.5f * g.dt_on_dx; P.alpha = g.alpha;
@@ -637,8 +642,9 @@ int launch_one_step(shll_ctx *c, int nsub = 1)
             S.want = c->round + 1;
             S.post = c->round + 2;
             S.epoch = c->sends + 1;
-            S.edge_warps_lo = 1;
-            S.edge_warps_hi = (unsigned)((g.nx - 1) / 120 - (g.nx - H) / 120 + 1);
+            // tiles owning one of the H outermost real cells of a side (shifted coordinates: real cell j sits at j + ext_lo)
+            S.edge_warps_lo = (unsigned)((H + ext_lo - 1) / 120 + 1);
+            S.edge_warps_hi = (unsigned)((g.nx + ext_lo - 1) / 120 - (g.nx - H + ext_lo) / 120 + 1);
         }
         P.sync = S;
         P.pdl = use_pdl(c);
@@ -658,7 +664,7 @@ int launch_one_step(shll_ctx *c, int nsub = 1)
             P.done = c->done;
             P.early_err = c->flags + 4;
         }
-        e = launch_step1d(c->key, P, grid, block, c->stream);
+        e = launch_step1d(c->key, P, grid, block, c->stream, nsub);
         if (e == cudaSuccess && P.early_blocks > 0) { c->early_epoch++; c->early_prev_grid = (int)grid.x; }
         sent = send;
     }
@@ -670,6 +676,21 @@ int launch_one_step(shll_ctx *c, int nsub = 1)
     c->launches++;
     if (sent) { c->round++; c->sends++; }
     return SHLL_OK;
+}
+
+// Steps the next launch advances: 2 where a two-step kernel exists for this context and at least two steps remain (1D slabs: and the
+// launch would not straddle the end of an exchange round).
+int next_nsub(const shll_ctx *c, long remaining)
+{
+    if (remaining < 2) return 1;
+    if (c->cfg.dims == 2) return c->fuse2 ? 2 : 1;
+    if (!c->fuse1d) return 1;
+    if (multi(c)) {
+        const int K = c->halo_K;
+        const int pos = (int)((c->state_index - c->origin) % (unsigned)K);
+        if (pos > K - 2) return 1;
+    }
+    return 2;
 }
 
 // Persistent 1D march: returns SHLL_E_STATE (without touching the error string) when the grid does not fit the scheme.
@@ -859,7 +880,8 @@ int shll_run(shll_ctx *c, long nsteps)
         if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
             int crc = SHLL_OK;
             c->capturing = true;
-            for (int s = 0; s < GRAPH_STEPS && crc == SHLL_OK; s += c->fuse2 ? 2 : 1) crc = launch_one_step(c, c->fuse2 ? 2 : 1);
+            const int gsub = next_nsub(c, GRAPH_STEPS);   // (single slab: the same for every launch of the graph)
+            for (int s = 0; s < GRAPH_STEPS && crc == SHLL_OK; s += gsub) crc = launch_one_step(c, gsub);
             c->capturing = false;
             cudaError_t e = cudaStreamEndCapture(c->stream, &g);
             if (crc == SHLL_OK && e == cudaSuccess && g) {
@@ -878,12 +900,13 @@ int shll_run(shll_ctx *c, long nsteps)
         }
         while (nsteps >= GRAPH_STEPS) {
             CK(c, cudaGraphLaunch(c->graph, c->stream));
-            c->state_index += GRAPH_STEPS; c->epoch += GRAPH_STEPS / (c->fuse2 ? 2 : 1); c->launches += GRAPH_STEPS / (c->fuse2 ? 2 : 1);
+            const int gsub = next_nsub(c, GRAPH_STEPS);
+            c->state_index += GRAPH_STEPS; c->epoch += GRAPH_STEPS / gsub; c->launches += GRAPH_STEPS / gsub;
             nsteps -= GRAPH_STEPS;
         }
     }
     while (nsteps > 0) {
-        const int nsub = (c->fuse2 && nsteps >= 2) ? 2 : 1;
+        const int nsub = next_nsub(c, nsteps);
         rc = launch_one_step(c, nsub);
         if (rc) return rc;
         nsteps -= nsub;

@@ -46,7 +46,7 @@ cudaError_t launch_step2d_tma_o2_strict(const KernelKey &k, const Step2DTmaParam
 cudaError_t launch_step2d_tma_o2_fast(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step2d_acc(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
 cudaError_t launch_step2d_acc2(const KernelKey &k, const Step2DTmaParams &p, dim3 grid, size_t smem, cudaStream_t s);
-cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s);
+cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s, int nsub = 1);
 
 // Persistent register-resident 1D march (cooperative launch; grid = nblocks, one block per SM).
 cudaError_t launch_persist1d(const KernelKey &k, const Persist1DParams &p, int nblocks, int threads, cudaStream_t s);

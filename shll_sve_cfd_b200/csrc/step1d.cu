@@ -13,8 +13,12 @@ static cudaError_t go(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3
 }
 
 template <int ORDER, int BC, int LIM>
-static cudaError_t by_mode(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s)
+static cudaError_t by_mode(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s, int nsub)
 {
+    if (nsub == 2) {  // two time steps per launch: FAST 2nd order only (step1d_acc.cuh: step1d_acc2_kernel)
+        if (!(k.mode == MODE_FAST && ORDER == 2 && k.acc)) return cudaErrorInvalidValue;
+        return launch_pdl(step1d_acc2_kernel<BC, LIM, 4>, grid, block, 0, s, p.pdl != 0, p);
+    }
     if (k.mode == MODE_FAST && ORDER == 2 && k.acc) {  // face-flux form, packed cell pairs (step1d_acc.cuh)
         const dim3 g4 = grid, b4 = block;
         switch (k.acc_cfg) {
@@ -28,16 +32,16 @@ static cudaError_t by_mode(const KernelKey &k, const Step1DParams &p, dim3 grid,
     return go<ORDER, BC, LIM, MODE_STRICT, TFORM_2D>(k, p, grid, block, s);
 }
 
-cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s)
+cudaError_t launch_step1d(const KernelKey &k, const Step1DParams &p, dim3 grid, dim3 block, cudaStream_t s, int nsub)
 {
     if (k.order == 1) {
-        if (k.bc == BC_REFLECT) return by_mode<1, BC_REFLECT, LIM_MINMOD>(k, p, grid, block, s);
-        return by_mode<1, BC_OUTFLOW, LIM_MINMOD>(k, p, grid, block, s);
+        if (k.bc == BC_REFLECT) return by_mode<1, BC_REFLECT, LIM_MINMOD>(k, p, grid, block, s, nsub);
+        return by_mode<1, BC_OUTFLOW, LIM_MINMOD>(k, p, grid, block, s, nsub);
     }
-    if (k.bc == BC_REFLECT && k.lim == LIM_MINMOD) return by_mode<2, BC_REFLECT, LIM_MINMOD>(k, p, grid, block, s);
-    if (k.bc == BC_REFLECT && k.lim == LIM_MC) return by_mode<2, BC_REFLECT, LIM_MC>(k, p, grid, block, s);
-    if (k.bc == BC_OUTFLOW && k.lim == LIM_MINMOD) return by_mode<2, BC_OUTFLOW, LIM_MINMOD>(k, p, grid, block, s);
-    if (k.bc == BC_OUTFLOW && k.lim == LIM_MC) return by_mode<2, BC_OUTFLOW, LIM_MC>(k, p, grid, block, s);
+    if (k.bc == BC_REFLECT && k.lim == LIM_MINMOD) return by_mode<2, BC_REFLECT, LIM_MINMOD>(k, p, grid, block, s, nsub);
+    if (k.bc == BC_REFLECT && k.lim == LIM_MC) return by_mode<2, BC_REFLECT, LIM_MC>(k, p, grid, block, s, nsub);
+    if (k.bc == BC_OUTFLOW && k.lim == LIM_MINMOD) return by_mode<2, BC_OUTFLOW, LIM_MINMOD>(k, p, grid, block, s, nsub);
+    if (k.bc == BC_OUTFLOW && k.lim == LIM_MC) return by_mode<2, BC_OUTFLOW, LIM_MC>(k, p, grid, block, s, nsub);
     return cudaErrorInvalidValue;
 }
 

@@ -37,30 +37,15 @@ __device__ __forceinline__ void cell_flux_1d_fast_x2g(const v2 (&u)[3], v2 (&fp)
     }
 }
 
-// The tile's three float4 are passed in (the kernel below streams them through a shared-memory ring).
+// One 2nd-order step of a lane's four cells (two packed pairs): split fluxes, limited face fluxes, update.  `u` -> `uo`.
+// Lanes 0 and 31 produce garbage in their outer two cells (no neighbour beyond the warp); their inner two are valid.
 template <int BC, int LIM, bool EDGE>
-__device__ __forceinline__ void step1d_acc_tile(const Step1DParams &P, int tile, int lane, const float4 (&in)[3])
+__device__ __forceinline__ void step1d_acc_update(const Step1DParams &P, int j0, int n, const v2 (&u)[2][3], v2 (&uo)[2][3])
 {
     constexpr int VEC = 4;
-    constexpr int USEFUL = 30 * VEC;
     const unsigned full = 0xffffffffu;
-    const int n = P.n;
-    const int j0 = tile * USEFUL + (lane - 1) * VEC;
     const bool lo_wall = P.lo_wall != 0, hi_wall = P.hi_wall != 0;
-    const int own_lo = tile * USEFUL, own_hi = min(own_lo + USEFUL, n);
-    const bool touch_lo = EDGE && (own_lo < P.xch), touch_hi = EDGE && (own_hi > n - P.xch) && (own_lo < n);
-    if (EDGE && P.sync.enabled && P.recv)
-        step1d_recv_halo(P, tile == 0, (long)tile * USEFUL + 124 > (long)P.ext_lo + P.n_real);
-
-    v2 u[2][3], fp[2][3], g[2][3];  // [pair][component]: pair 0 = cells j0, j0+1; pair 1 = cells j0+2, j0+3
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-        float4 t = in[k];
-        // an EDGE tile may read halo cells a neighbour GPU has only just written: load it (again) AFTER the halo wait above
-        if (EDGE) t = *reinterpret_cast<const float4 *>(P.in[k] + min(j0, ((n + 3) & ~3)));
-        u[0][k] = v2mk(t.x, t.y);
-        u[1][k] = v2mk(t.z, t.w);
-    }
+    v2 fp[2][3], g[2][3];  // [pair][component]: pair 0 = cells j0, j0+1; pair 1 = cells j0+2, j0+3
     cell_flux_1d_fast_x2g(u[0], fp[0], g[0]);
     cell_flux_1d_fast_x2g(u[1], fp[1], g[1]);
 
@@ -78,8 +63,6 @@ __device__ __forceinline__ void step1d_acc_tile(const Step1DParams &P, int tile,
         q[0] = v2mk(qs[0], qs[1]); q[1] = v2mk(qs[2], qs[3]);
         nq[0] = v2neg(q[0]); nq[1] = v2neg(q[1]);
     }
-
-    v2 uo[2][3];
 #pragma unroll
     for (int k = 0; k < 3; k++) {
         // backward differences d[j] = F[j] - F[j-1]; the forward difference of cell j is d[j+1]
@@ -114,6 +97,43 @@ __device__ __forceinline__ void step1d_acc_tile(const Step1DParams &P, int tile,
         uo[0][k] = v2fma(v2bc(-P.dtdx), v2add(s0, t0), u[0][k]);
         uo[1][k] = v2fma(v2bc(-P.dtdx), v2add(s1, t1), u[1][k]);
     }
+}
+
+// The tile's three float4 are passed in (the kernel below streams them through a shared-memory ring).  NSUB = 2: two time steps
+// per launch -- the lane's four halo cells are exactly the reach of two 2nd-order steps, so the second step runs on the first
+// one's result in registers (valid on the 120 owned cells); HBM sees one read and one write per two steps.  The slab machinery
+// (step1d.cuh) is unchanged: such a launch sits at round positions (p, p + 1), the host extends the range for position p.
+template <int BC, int LIM, bool EDGE, int NSUB>
+__device__ __forceinline__ void step1d_acc_tile(const Step1DParams &P, int tile, int lane, const float4 (&in)[3])
+{
+    constexpr int VEC = 4;
+    constexpr int USEFUL = 30 * VEC;
+    const int n = P.n;
+    const int j0 = tile * USEFUL + (lane - 1) * VEC;
+    const int own_lo = tile * USEFUL, own_hi = min(own_lo + USEFUL, n);
+    // real (unshifted) cell indices: send steps may run on an extended range (ext_lo > 0 when two steps share a launch)
+    const int e = P.ext_lo, nr = P.n_real;
+    const bool touch_lo = EDGE && P.xch > 0 && (own_lo - e < P.xch) && (own_hi - e > 0);
+    const bool touch_hi = EDGE && P.xch > 0 && (own_hi - e > nr - P.xch) && (own_lo - e < nr);
+    if (EDGE && P.sync.enabled && P.recv)
+        step1d_recv_halo(P, tile == 0, (long)tile * USEFUL + 124 > (long)P.ext_lo + P.n_real);
+
+    v2 u[2][3], uo[2][3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+        float4 t = in[k];
+        // an EDGE tile may read halo cells a neighbour GPU has only just written: load it (again) AFTER the halo wait above
+        if (EDGE) t = *reinterpret_cast<const float4 *>(P.in[k] + min(j0, ((n + 3) & ~3)));
+        u[0][k] = v2mk(t.x, t.y);
+        u[1][k] = v2mk(t.z, t.w);
+    }
+    if (NSUB == 1) {
+        step1d_acc_update<BC, LIM, EDGE>(P, j0, n, u, uo);
+    } else {
+        v2 um[2][3];
+        step1d_acc_update<BC, LIM, EDGE>(P, j0, n, u, um);
+        step1d_acc_update<BC, LIM, EDGE>(P, j0, n, um, uo);
+    }
 
     if (!EDGE) {  // interior tile: every owner lane stores three full float4
         if (lane != 0 && lane != 31) {
@@ -135,16 +155,17 @@ __device__ __forceinline__ void step1d_acc_tile(const Step1DParams &P, int tile,
             for (int v = 0; v < VEC; v++)
                 if (j0 + v < n) P.out[k][j0 + v] = o[v];
         }
-        // halo exchange fused into the step: edge cells go straight into the neighbour GPU's halo cells
-        if (P.lo_peer[k] != nullptr && j0 < P.xch) {
+        // halo exchange fused into the step: the outermost xch real cells go straight into the neighbour GPU's mailbox
+        const int jr = j0 - e;
+        if (P.lo_peer[k] != nullptr && jr < P.xch) {
 #pragma unroll
             for (int v = 0; v < VEC; v++)
-                if (j0 + v < P.xch && j0 + v < n) P.lo_peer[k][j0 + v] = o[v];
+                if (jr + v >= 0 && jr + v < P.xch && jr + v < nr) P.lo_peer[k][jr + v] = o[v];
         }
-        if (P.hi_peer[k] != nullptr && j0 + VEC > n - P.xch) {
+        if (P.hi_peer[k] != nullptr && jr + VEC > nr - P.xch) {
 #pragma unroll
             for (int v = 0; v < VEC; v++)
-                if (j0 + v >= n - P.xch && j0 + v < n) P.hi_peer[k][j0 + v - (n - P.xch)] = o[v];
+                if (jr + v >= nr - P.xch && jr + v < nr) P.hi_peer[k][jr + v - (nr - P.xch)] = o[v];
         }
     }
     if (P.sync.enabled) {
@@ -158,9 +179,20 @@ template <int BC, int LIM, int MINB>
 __global__ void __launch_bounds__(128, MINB) step1d_acc_kernel(const Step1DParams P)
 {
     step1d_ring_march(P, [&](int tile, int lane, bool interior, const float4(&cur)[3]) {
-        if (interior) step1d_acc_tile<BC, LIM, false>(P, tile, lane, cur);
-        else step1d_acc_tile<BC, LIM, true>(P, tile, lane, cur);
+        if (interior) step1d_acc_tile<BC, LIM, false, 1>(P, tile, lane, cur);
+        else step1d_acc_tile<BC, LIM, true, 1>(P, tile, lane, cur);
     }, 2);
+}
+
+// Two time steps per launch (see step1d_acc_tile).  `order` = 4 for the interior test: a tile is interior when the two-step
+// reach of its 128 loaded cells stays inside the owned cells.
+template <int BC, int LIM, int MINB>
+__global__ void __launch_bounds__(128, MINB) step1d_acc2_kernel(const Step1DParams P)
+{
+    step1d_ring_march(P, [&](int tile, int lane, bool interior, const float4(&cur)[3]) {
+        if (interior) step1d_acc_tile<BC, LIM, false, 2>(P, tile, lane, cur);
+        else step1d_acc_tile<BC, LIM, true, 2>(P, tile, lane, cur);
+    }, 4);
 }
 
 }  // namespace shll

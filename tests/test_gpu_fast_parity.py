@@ -92,7 +92,7 @@ def test_fast_1d_64m_cells_benched_kernel_window_vs_oracle(oracle):
     pb = programs.SECOND_ORDER_1D.resized(n)
     u0 = programs.cons_from_prim(pb, programs.initial_primitives(pb))
     got, name, launches = _fast_run(pb, u0, steps)
-    assert "_acc_" in name and launches == steps, (name, launches)
+    assert "_acc_" in name and name.endswith("_x2") and launches == steps // 2, (name, launches)
     i0 = n // 2 - W // 2
     sub = programs.SECOND_ORDER_1D.resized(W)
     ref = oracle.run(oracle_cfg_for(oracle, sub), np.ascontiguousarray(u0[:, i0:i0 + W]), steps)
@@ -203,6 +203,39 @@ def test_fused_two_step_launches_give_the_bits_of_single_steps(shape, bc, monkey
             g.run(7); g.run(2); g.run(1); g.run(12)
             assert g.variant(0).endswith("_x2"), g.variant(0)
             assert np.array_equal(bits(g.download_u()), bits(base[0])), "3 slabs with two-step launches differ from one slab"
+
+
+@pytest.mark.parametrize("n", [121, 1000, 4099, 30000, 200000])
+@pytest.mark.parametrize("scheme", ["1d_o2_outflow", "1d_o2_reflect_mc"])
+def test_fused_two_step_1d_launches_give_the_bits_of_single_steps(n, scheme, monkeypatch):
+    """1D 2nd-order FAST: two steps per launch (csrc/step1d_acc.cuh, NSUB = 2) -- the second step runs on the first one's result
+    in registers.  Same bits as one launch per step: walls (reflect) and outflow ends, MC limiter, ragged sizes, odd and split
+    step counts; and through slabs sharing a device with exchange rounds of 2, 4 and 16 steps (a two-step launch never straddles
+    a round; the send launch runs on a range extended by the first step's halo cells)."""
+    monkeypatch.setenv("SHLL_PERSIST", "0")
+    monkeypatch.setenv("SHLL_GRAPH", "0")
+    pb = SCHEMES[scheme].resized(n)
+    u0 = _random_state(pb, seed=n % 89)
+    outs = {}
+    for fuse in ("0", "1"):
+        monkeypatch.setenv("SHLL_FUSE1D", fuse)
+        with programs.make_solver(pb, capi.MODE_FAST) as s:
+            s.upload_u(u0)
+            s.run(7); s.run(2); s.run(1); s.run(12)
+            outs[fuse] = (s.download_u(), s.variant, s.launches)
+    assert outs["0"][2] == 22 and outs["1"][2] == 4 + 1 + 1 + 6 and outs["1"][1].endswith("_x2")
+    assert np.array_equal(bits(outs["0"][0]), bits(outs["1"][0])), f"N={n} {scheme}"
+    if n >= 1000:
+        _, _, _, dtdx, _ = programs.time_constants(pb)
+        for K in ("2", "4", "16"):
+            monkeypatch.setenv("SHLL_FUSE1D", "1")
+            monkeypatch.setenv("SHLL_HALO_K", K)
+            with capi.Group(1, pb.nx, 1, ngpus=3, devices=[0, 0, 0], order=2, bc=pb.bc, limiter=pb.limiter, tform=pb.tform, mode=capi.MODE_FAST,
+                            alpha=pb.alpha, dt_on_dx=float(dtdx)) as g:
+                g.upload_u(u0)
+                g.run(7); g.run(2); g.run(1); g.run(12)
+                assert g.variant(0).endswith("_x2")
+                assert np.array_equal(bits(g.download_u()), bits(outs["0"][0])), f"N={n} {scheme}: 3 slabs, rounds of {K} steps"
 
 
 # ------------------------------------------------------------------------------------ full-length FAST runs
