@@ -561,7 +561,8 @@ def workload_block(h, name, r, K):
             "timed_region_s": r["region_s"], "value": r["value"], "unit": UNIT, "ms_per_step": r["ms"] / K,
             "ms_per_step_min_max": [r["ms_min"] / K, r["ms_max"] / K],
             "roofline": {"bound": "hbm", "achieved": r["achieved"], "peak": r["peak"], "unit": "GB/s", "frac": r["achieved"] / r["peak"],
-                         "traffic": tr, "traffic_source": tr_src, "algorithmic_bytes_per_step": r["bytes_per_launch"]},
+                         "traffic": tr, "traffic_source": tr_src, "algorithmic_bytes_per_step": r["bytes_per_launch"],
+                         "steps_per_launch": max(1, K // max(1, r["launches"])) if r["launches"] > 1 else None},
             "clocks": r["clocks"], "parity_vs_1gpu": r.get("parity_vs_1gpu"), "halo_exchange": r.get("halo"), **per_launch_note}
 
 
