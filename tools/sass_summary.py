@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "shll_sve_cfd_b200", "libshll_b200.so")
 OPS = ["UTMALDG", "UTMASTG", "SYNCS", "LDGSTS", "FFMA2", "FMUL2", "FADD2", "FFMA", "DFMA", "DMUL", "MUFU", "LOP3", "FMNMX", "SHFL",
        "STG", "STS", "LDS", "MEMBAR"]
-HOT = [r"step2d_acc_kernelILi1ELi0ELi0ELi16ELi0E", r"step2d_acc_kernelILi2ELi1ELi0ELi12ELi0E", r"step2d_acc_kernelILi2ELi1ELi1ELi12ELi0E",
+HOT = [r"step2d_acc2_kernelILi0ELi12E", r"step1d_acc2_kernelILi1ELi0ELi4E", r"step2d_acc_kernelILi1ELi0ELi0ELi16ELi0E", r"step2d_acc_kernelILi2ELi1ELi0ELi12ELi0E", r"step2d_acc_kernelILi2ELi1ELi1ELi12ELi0E",
        r"step1d_acc_kernelILi1ELi0ELi6E", r"step1d_kernelILi1ELi0ELi0ELi1ELi2ELb1E", r"step1d_kernelILi2ELi1ELi0ELi0ELi2ELb1E",
        r"step1d_kernelILi1ELi0ELi0ELi0ELi1ELb1E", r"persist1d_kernelILi2ELi1ELi0ELi1ELi2ELb1E", r"persist1d_kernelILi2ELi1ELi0ELi0ELi2ELb1E",
        r"step2d_tma_kernelILi1ELi0ELi0ELi0ELi1ELb1E", r"step2d_tma_kernelILi2ELi1ELi0ELi0ELi1ELb1E"]
