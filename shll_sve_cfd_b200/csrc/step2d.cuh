@@ -487,7 +487,7 @@ __global__ void __launch_bounds__(128) step2d_kernel(const __grid_constant__ Ste
     const bool touch_lo = (X.r0 < ORDER), touch_hi = (X.r1 > nx - ORDER);
     if (P.sync.enabled) {  // wait until the neighbour GPUs' edge rows of the previous step sit in our halo rows
         if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
-        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
+        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi, 1);
     }
 
     if (ORDER == 1) {

@@ -260,8 +260,8 @@ __global__ void __launch_bounds__(32) step2d_tma_kernel(const __grid_constant__ 
     const int rmin = P.lo_wall ? 0 : -2;
     const bool touch_lo = (X.r0 < ORDER), touch_hi = (X.r1 > nx - ORDER);
     if (P.sync.enabled) {  // the neighbour GPUs' edge rows of the previous step must sit in our halo rows
-        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo);
-        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi);
+        if (touch_lo) halo_wait(P.sync, P.sync.wait_lo, 0);
+        if (touch_hi) halo_wait(P.sync, P.sync.wait_hi, 1);
     }
 
     // ---- ring set-up

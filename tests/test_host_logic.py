@@ -260,3 +260,26 @@ def test_shared_reciprocal_float_division_is_correctly_rounded_in_exact_arithmet
         q = R24(q0 + r * rem)
         bad += (q != R24(a / b))
     assert bad == 0
+
+
+def test_plan_halo_steps_is_one_value_for_the_whole_chain_of_slabs(monkeypatch):
+    """shll_plan_halo_steps (include/shll_b200.h): steps per halo exchange round from the WHOLE domain, so that every slab of a
+    balanced partition gets the same value -- 1D: K*order <= 32 cells and <= the smallest slab; 2D: 2 (two-step launches, two-row
+    exchange) only where the 1st-order FAST face-flux kernel is selected and every slab has >= 16 rows.  Pure host logic: no GPU."""
+    monkeypatch.delenv("SHLL_HALO_K", raising=False)
+    plan = capi.plan_halo_steps
+    F, S = capi.MODE_FAST, capi.MODE_STRICT
+    assert plan(1, 1 << 26, 1, 2, F, 8) == 16 and plan(1, 1 << 26, 1, 1, F, 8) == 16      # order 2: 32 cells; order 1: 16 cells
+    assert plan(1, 1 << 26, 1, 2, F, 1) == 1                                               # one slab: nothing to exchange
+    assert plan(1, 40, 1, 2, F, 8) == 2 and plan(1, 15, 1, 2, S, 3) == 2 and plan(1, 9, 1, 1, S, 3) == 3   # limited by the smallest slab
+    assert plan(1, 6, 1, 2, S, 3) == 1
+    monkeypatch.setenv("SHLL_HALO_K", "5")
+    assert plan(1, 1 << 20, 1, 2, F, 4) == 5
+    monkeypatch.delenv("SHLL_HALO_K")
+    assert plan(2, 8 * 4096, 4096, 1, F, 8) == 2                   # configs[2] weak-scaled: two-step launches
+    assert plan(2, 8 * 4096, 4096, 1, S, 8) == 1                   # STRICT: one step per launch
+    assert plan(2, 16384, 16384, 2, F, 8) == 1                     # 2nd order: one step per launch
+    assert plan(2, 8 * 4096, 4100, 1, F, 8) == 1                   # ny % 8 != 0: not the face-flux kernel
+    assert plan(2, 8 * 15, 256, 1, F, 8) == 1 and plan(2, 8 * 16, 256, 1, F, 8) == 2      # slabs thinner than 16 rows keep one step
+    monkeypatch.setenv("SHLL_FUSE2", "0")
+    assert plan(2, 8 * 4096, 4096, 1, F, 8) == 1
