@@ -1,5 +1,5 @@
 #!/bin/bash
-# round-2 ncu evidence: one --set full capture per hot kernel + the launch list of the default bench command
+# usage: gpurun -- tools/ncu_evidence.sh    round-2 ncu evidence: one --set full capture per hot kernel + the launch list of the default bench command
 O=gpurun_out; mkdir -p $O
 prof() {  # name regex workload mode cells
   local name=$1 rx=$2 wl=$3 mode=$4 cells=$5
@@ -10,10 +10,12 @@ prof() {  # name regex workload mode cells
   ncu -i $O/r02_$name.ncu-rep --page source --csv 2>/dev/null | gzip > $O/r02_$name.source.csv.gz
   rm -f $O/r02_$name.ncu-rep
 }
-prof 2d_o1_acc_fast 'step2d_acc' 2d_o1 fast 16777216
+prof 2d_o1_acc2_fast 'step2d_acc2' 2d_o1 fast 33554432      # two steps per launch: cells x 2
+SHLL_FUSE2=0 prof 2d_o1_acc_fast 'step2d_acc' 2d_o1 fast 16777216
 prof 2d_o2_acc_fast 'step2d_acc' 2d_o2 fast 33554432
 prof 2d_o1_tma_strict 'step2d_tma' 2d_o1 strict 16777216
-prof 1d_o2_acc_fast 'step1d' 1d_o2 fast 67108864
+prof 1d_o2_acc2_fast 'step1d_acc2' 1d_o2 fast 134217728
+SHLL_FUSE1D=0 prof 1d_o2_acc_fast 'step1d' 1d_o2 fast 67108864
 echo "== launch list of the default bench command (short)"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/r02_launches_bench_default.csv \
   python bench.py --steps 20 --warmup 5 --no-cpu-baseline > $O/r02_launches_bench.log 2>&1

@@ -1,5 +1,5 @@
 #!/bin/bash
-# 8-GPU box: multi-GPU parity with the final kernels + the driver-style line at N = 8 and N = 1
+# usage: gpurun --gpus 8 -- tools/scale8.sh    multi-GPU parity (2, 4, 8 GPUs) + the driver-style bench line at N = 8 and N = 1 on ONE box -> gpurun_out/r02_scale_n{1,8}.json
 O=gpurun_out; mkdir -p $O
 timeout 1200 python -m pytest tests/test_multi_gpu.py -x -q 2>&1 | tail -3 | tee $O/r2_25_pytest_mgpu.log
 N=8
