@@ -364,7 +364,7 @@ def traffic_entry(key):
         e = t.get(key)
         if isinstance(e, dict):
             return e.get("bytes"), e.get("source")
-        return e, t.get("_source")
+        return (e, t.get("_source")) if e is not None else (None, None)
     except Exception:
         return None, None
 
